@@ -1,0 +1,198 @@
+/*
+ * mudiff_b200.h - C ABI of libmudiff_b200.so (hand-written sm_100a CUDA kernels for the
+ * MU-Diff reverse-sampling hot path).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; inputs are borrowed, outputs are
+ *     caller-allocated (the reference allocates with at::empty inside its op,
+ *     utils/op/upfirdn2d_kernel.cu:244-245; here the Python wrapper allocates with torch);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and
+ *     CUDA-graph-capture safe (no allocation, no host<->device copy, no sync);
+ *   - return value: 0 = launched, >0 = cudaError_t of the launch, <0 = -EINVAL style
+ *     argument reject (MUDIFF_EINVAL / MUDIFF_EUNSUPPORTED).  Nothing falls back to CPU;
+ *   - dtype codes: MUDIFF_F32 = 0, MUDIFF_BF16 = 1, MUDIFF_F16 = 2;
+ *   - activations are NHWC ("channels_last"): element (b,y,x,c) at ((b*H+y)*W+x)*ld + c.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * MU-Diff repository root).
+ */
+#ifndef MUDIFF_B200_H
+#define MUDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUDIFF_F32 0
+#define MUDIFF_BF16 1
+#define MUDIFF_F16 2
+
+#define MUDIFF_EINVAL (-22)
+#define MUDIFF_EUNSUPPORTED (-95)
+
+#define MUDIFF_ACT_NONE 0
+#define MUDIFF_ACT_SILU 1
+#define MUDIFF_ACT_SIGMOID 2
+#define MUDIFF_ACT_TANH 3
+
+/* ABI version + build info (static string). */
+int mudiff_abi_version(void);
+const char* mudiff_build_info(void);
+/* Number of kernels launched by this library since load (for bench.py `gpu_launches`). */
+int64_t mudiff_launch_count(void);
+/* sizeof(mudiff_conv_desc) as compiled, so bindings can verify their struct layout. */
+int mudiff_conv_desc_size(void);
+
+/* ---------------------------------------------------------------------------------
+ * FIR resampling.  Replaces upfirdn2d_op.upfirdn2d(input[major,H,W,minor], kernel[kh,kw],
+ * up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)  (utils/op/upfirdn2d.cpp:20-31,
+ * utils/op/upfirdn2d_kernel.cu:211-371).  Same semantics: zero-insert upsample, pad
+ * (negative = crop), TRUE convolution with `kernel` (the kernel is flipped, :139),
+ * decimate.  out is [major, out_h, out_w, minor], out_h = (in_h*up_y+pad_y0+pad_y1-kh)/down_y+1.
+ * NCHW tensors use major=N*C, minor=1 (what utils/op/upfirdn2d.py:124 does); NHWC tensors
+ * use major=N, minor=C (vectorised path when minor % 8 == 0).
+ * `kernel` is float32 on the device regardless of dtype.  kh,kw <= 32.
+ * ------------------------------------------------------------------------------- */
+int mudiff_upfirdn2d(const void* in, void* out, const float* kernel, int dtype,
+                     int64_t major, int in_h, int in_w, int minor, int kh, int kw,
+                     int up_x, int up_y, int down_x, int down_y,
+                     int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream);
+
+/* Replaces fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ * (utils/op/fused_bias_act.cpp:18-27, fused_bias_act_kernel.cu:20-51):
+ *   x += bias[(i / step_b) % size_b] (if bias); act 1 = linear, 3 = leaky-relu(alpha);
+ *   grad 0: y = act(x)*scale; grad 1: y = x * dact(ref) * scale; grad 2: 0 (second order).
+ * bias/ref may be NULL. */
+int mudiff_fused_bias_act(const void* x, const void* bias, const void* ref, void* out, int dtype,
+                          int64_t n, int size_b, int64_t step_b, int act, int grad,
+                          float alpha, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Posterior update, one fused kernel.  Replaces sample_posterior_combine
+ * (engine/test.py:150-177):  mean = ((c1[t]*x01 + c2[t]*xt) + (c1[t]*x02 + c2[t]*xt))/2,
+ * out = mean + (t!=0) * exp(0.5*logvar[t]) * noise.   All fp32; t is int64 [B];
+ * c1/c2/logvar are fp32 device tables of length n_steps; per_sample = C*H*W;
+ * x01/x02 may be channel-0 slices of wider tensors: sample stride given in elements.
+ * ------------------------------------------------------------------------------- */
+int mudiff_posterior_update(const float* x01, int64_t x01_bstride, const float* x02, int64_t x02_bstride,
+                            const float* xt, const float* noise, const int64_t* t,
+                            const float* coef1, const float* coef2, const float* logvar, int n_steps,
+                            float* out, int batch, int64_t per_sample, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * GroupNorm (+ AdaGN scale/shift) (+ SiLU).  Replaces AdaptiveGroupNorm.forward
+ * (backbones/layerspp.py:47-54), GroupNorm_Conv (:56-65), nn.GroupNorm call sites
+ * (:103,:113; ncsnpp_generator_adagn_feat.py:265,436) and the following self.act.
+ * Input is the channel-concatenation of up to two NHWC tensors (x0: C0 channels with
+ * pixel stride ld0, x1: C1 with ld1; x1 may be NULL) - this is torch.cat([h, hs.pop()], 1)
+ * of ncsnpp_generator_adagn_feat.py:383 without materialising it.
+ * stats: double[B][G][2] = (sum, sum of squares); mudiff_gn_stats ACCUMULATES into it
+ * (caller zeroes it, e.g. with mudiff_zero).  G groups over C0+C1 channels.
+ * apply: y = act(gamma[b,c] * (x-mean)*rstd + beta[b,c]); gamma/beta fp32 with batch
+ * stride gb_bstride (0 => shared affine [C]); NULL gamma/beta => 1/0.
+ * ------------------------------------------------------------------------------- */
+int mudiff_gn_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int dtype,
+                    int batch, int64_t hw, int groups, double* stats, void* stream);
+int mudiff_gn_apply(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int dtype_in,
+                    const double* stats, const float* gamma, const float* beta, int64_t gb_bstride,
+                    void* out, int ld_out, int dtype_out, int batch, int64_t hw, int groups,
+                    float eps, int act, void* stream);
+int mudiff_zero(void* p, int64_t nbytes, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Convolution / contraction descriptor shared by the tensor-core and SIMT kernels.
+ * Replaces the nn.Conv2d / F.conv2d / NIN / einsum call sites of the generator
+ * (backbones/layers.py:124,502-505; backbones/layerspp.py:118,122;
+ *  backbones/up_or_down_sampling.py:183).
+ *
+ *  out[b,y,x,coff+n] = act( alpha * ( sum_seg sum_tap sum_c A_seg[b, y*s+dy, x*s+dx, c] * Wt[n, k(seg,tap,c)]
+ *                                     + bias[n] + rowbias[b,n] ) + beta * residual[b,y,x,n] )
+ *
+ * A segments: up to 3 NHWC tensors with identical B,H,W (channel concat and the fused
+ * 1x1 shortcut of ResnetBlockBigGANpp_Adagn, layerspp.py:318-324).  taps = 9 (3x3, pad 1)
+ * or 1 (1x1).  Weights are packed [w_batch][N][Ktot] (K-major) with
+ * k = seg_offset + tap*C_seg + c;  w_bstride = 0 => shared weights, else elements between
+ * per-sample weight matrices (attention QK^T / PV).  a_bstride0 = 1 => segment tensors
+ * are per-sample (normal); 0 => A shared across the batch (swapped GEMM, A = weights).
+ * ------------------------------------------------------------------------------- */
+typedef struct mudiff_conv_desc {
+  const void* a[3];        /* NHWC tensors                                         */
+  int32_t a_c[3];          /* channels used from each                              */
+  int32_t a_ld[3];         /* pixel stride (elements) of each                      */
+  int32_t a_taps[3];       /* 9 or 1                                               */
+  int32_t nseg;
+  int32_t a_batched;       /* 1: A indexed by b; 0: A shared over batch            */
+  int32_t batch, h, w;     /* INPUT spatial size (output too when stride == 1)     */
+  int32_t stride;          /* 1, or 2 (SIMT only; pad 0: conv_downsample_2d)       */
+  int32_t pad;             /* 1 for 3x3 'same', 0 for 1x1 / strided                */
+  const void* wt;          /* packed weights, dtype = a dtype                      */
+  int64_t w_bstride;
+  int32_t w_ld;            /* row stride of wt in elements; 0 => Ktot              */
+  int32_t n;               /* output channels                                      */
+  const float* bias;       /* [n] or NULL                                          */
+  const float* rowbias;    /* [batch][rowbias_ld] or NULL (Dense_0(act(temb)))     */
+  int32_t rowbias_ld;
+  const void* residual;    /* NHWC [.., res_ld] dtype = out dtype, or NULL         */
+  int32_t res_ld;
+  float alpha, beta;
+  int32_t act;             /* MUDIFF_ACT_*                                         */
+  void* out;
+  int32_t out_ld, out_coff;
+  int32_t out_dtype;
+  double* stats;           /* optional fused GroupNorm statistics of the OUTPUT    */
+  int32_t stats_groups;    /*   (sum,sumsq)[batch][groups], accumulated; or NULL   */
+  int32_t flags;           /* bit0: force halo mode, bit1: forbid halo mode,
+                              bit2: descriptor base-offset variant (debug)         */
+} mudiff_conv_desc;
+
+/* tcgen05/TMEM/TMA implicit GEMM (bf16 in, fp32 accumulate).  Requires a_c[i] % 64 == 0,
+ * n % 32 == 0, stride == 1.  Returns MUDIFF_EUNSUPPORTED otherwise. */
+int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream);
+/* CUDA-core implicit GEMM (fp32 or bf16 storage, fp32 math): any shape, stride 1/2.
+ * This is the fp32-parity path and the path for Cin=1 / Cout=1 / strided convs. */
+int mudiff_conv_simt(const mudiff_conv_desc* d, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Attention pieces (backbones/layerspp.py:118-122).
+ * Row softmax, in place allowed: y[r,:] = softmax(scale * x[r,:]) over `cols`.
+ * ------------------------------------------------------------------------------- */
+int mudiff_softmax_rows(const void* x, void* y, int dtype, int64_t rows, int cols, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Small dense layers on embeddings (nn.Linear call sites: dense_layer.py:67-71,
+ * ncsnpp_generator_adagn_feat.py:105-110,271-277; layerspp.py:42,277).
+ * out[b,j] = act_out( sum_k act_in(in[b,k]) * W[j,k] + bias[j] ), all fp32.
+ * Batched over many layers by concatenating W rows.
+ * ------------------------------------------------------------------------------- */
+int mudiff_linear(const float* in, int in_ld, const float* w, const float* bias, float* out, int out_ld,
+                  int batch, int k, int j, int act_in, int act_out, void* stream);
+/* layers.py:465-479 get_timestep_embedding(t int64 [B], dim) -> fp32 [B, dim] */
+int mudiff_timestep_embedding(const int64_t* t, float* out, int batch, int dim, float max_positions, void* stream);
+/* PixelNorm (ncsnpp_generator_adagn_feat.py:44-49): z / sqrt(mean(z^2, dim=1) + 1e-8) */
+int mudiff_pixelnorm(const float* z, float* out, int batch, int dim, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Elementwise glue on NHWC tensors (dtype f32/bf16), n = number of elements.
+ *   gate_mul   : out = a * b                          (ncsnpp_generator_adagn_feat.py:778)
+ *   gate_blend : out = g*a + (1-g)*b                  (:779), out written at channel offset
+ *   add_scale  : out = (a + b) * scale                (:363 input-pyramid residual)
+ *   copy_channels : dst[p, coff:coff+c] = src[p, 0:c] (torch.cat)
+ *   gap        : out[b,c] = mean_p x[b,p,c]  fp32     (layerspp.py:473,491)
+ *   cast       : dtype conversion / strided channel copy
+ * ------------------------------------------------------------------------------- */
+int mudiff_gate_mul(const void* a, int a_ld, const void* b, int b_ld, void* out, int out_ld,
+                    int dtype, int64_t pixels, int c, void* stream);
+int mudiff_gate_blend(const void* g, int g_ld, const void* a, int a_ld, const void* b, int b_ld,
+                      void* out, int out_ld, int dtype, int64_t pixels, int c, void* stream);
+int mudiff_add_scale(const void* a, const void* b, void* out, int dtype, int64_t n, float scale, void* stream);
+int mudiff_copy_channels(const void* src, int src_ld, int src_dtype, void* dst, int dst_ld, int dst_dtype,
+                         int64_t pixels, int c, void* stream);
+int mudiff_gap(const void* x, int ld, int dtype, float* out, int batch, int64_t hw, int c, void* stream);
+int mudiff_tanh(const void* x, void* out, int dtype_in, int dtype_out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUDIFF_B200_H */

@@ -1,0 +1,118 @@
+"""ctypes binding of libmudiff_b200.so (C ABI declared in include/mudiff_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `csrc/Makefile`.  There is no
+CPU or PyTorch fallback: if the shared object is missing or a launch is rejected the
+caller gets a RuntimeError (the reference raises RuntimeError("CUDA upfirdn2d extension
+not available"), utils/op/upfirdn2d.py:114-115).
+"""
+import ctypes as C
+import os
+
+import torch
+
+F32, BF16, F16 = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
+EINVAL, EUNSUPPORTED = -22, -95
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmudiff_b200.so')
+
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+
+class ConvDesc(C.Structure):
+    """struct mudiff_conv_desc (include/mudiff_b200.h)."""
+    _fields_ = [
+        ('a', C.c_void_p * 3), ('a_c', C.c_int32 * 3), ('a_ld', C.c_int32 * 3), ('a_taps', C.c_int32 * 3),
+        ('nseg', C.c_int32), ('a_batched', C.c_int32),
+        ('batch', C.c_int32), ('h', C.c_int32), ('w', C.c_int32),
+        ('stride', C.c_int32), ('pad', C.c_int32),
+        ('wt', C.c_void_p), ('w_bstride', C.c_int64), ('w_ld', C.c_int32), ('n', C.c_int32),
+        ('bias', C.c_void_p), ('rowbias', C.c_void_p), ('rowbias_ld', C.c_int32),
+        ('residual', C.c_void_p), ('res_ld', C.c_int32),
+        ('alpha', C.c_float), ('beta', C.c_float), ('act', C.c_int32),
+        ('out', C.c_void_p), ('out_ld', C.c_int32), ('out_coff', C.c_int32), ('out_dtype', C.c_int32),
+        ('stats', C.c_void_p), ('stats_groups', C.c_int32), ('flags', C.c_int32),
+    ]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> argtypes  (restype is int unless listed in _RESTYPES)
+PROTOTYPES = {
+    'mudiff_abi_version': [],
+    'mudiff_build_info': [],
+    'mudiff_launch_count': [],
+    'mudiff_conv_desc_size': [],
+    'mudiff_upfirdn2d': [_P, _P, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'mudiff_fused_bias_act': [_P, _P, _P, _P, _I, _L, _I, _L, _I, _I, _F, _F, _P],
+    'mudiff_posterior_update': [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _P, _I, _L, _P],
+    'mudiff_gn_stats': [_P, _I, _I, _P, _I, _I, _I, _I, _L, _I, _P, _P],
+    'mudiff_gn_apply': [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _L, _P, _I, _I, _I, _L, _I, _F, _I, _P],
+    'mudiff_zero': [_P, _L, _P],
+    'mudiff_conv_tc': [C.POINTER(ConvDesc), _P],
+    'mudiff_conv_simt': [C.POINTER(ConvDesc), _I, _P],
+    'mudiff_softmax_rows': [_P, _P, _I, _L, _I, _F, _P],
+    'mudiff_linear': [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'mudiff_timestep_embedding': [_P, _P, _I, _I, _F, _P],
+    'mudiff_pixelnorm': [_P, _P, _I, _I, _P],
+    'mudiff_gate_mul': [_P, _I, _P, _I, _P, _I, _I, _L, _I, _P],
+    'mudiff_gate_blend': [_P, _I, _P, _I, _P, _I, _P, _I, _I, _L, _I, _P],
+    'mudiff_add_scale': [_P, _P, _P, _I, _L, _F, _P],
+    'mudiff_copy_channels': [_P, _I, _I, _P, _I, _I, _L, _I, _P],
+    'mudiff_gap': [_P, _I, _I, _P, _I, _L, _I, _P],
+    'mudiff_tanh': [_P, _P, _I, _I, _L, _P],
+}
+_RESTYPES = {'mudiff_build_info': C.c_char_p, 'mudiff_launch_count': C.c_int64}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"mu-diff_b200: {LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C mu-diff_b200/csrc`). There is no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(l, name)           # AttributeError if the .so does not export a declared symbol
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        if l.mudiff_conv_desc_size() != C.sizeof(ConvDesc):
+            raise RuntimeError('mu-diff_b200: ConvDesc layout mismatch between _lib.py and the shared library')
+        _lib = l
+    return _lib
+
+
+def dtype_code(t: torch.dtype) -> int:
+    try:
+        return _DTYPES[t]
+    except KeyError:
+        raise RuntimeError(f"mu-diff_b200: unsupported dtype {t}") from None
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc == EINVAL:
+        raise RuntimeError(f"mu-diff_b200: {what}: invalid argument")
+    if rc == EUNSUPPORTED:
+        raise RuntimeError(f"mu-diff_b200: {what}: unsupported shape/dtype for this kernel")
+    raise RuntimeError(f"mu-diff_b200: {what}: CUDA error {rc}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mu-diff_b200: expected CUDA tensors (this package has no CPU path)")
+
+
+def launch_count() -> int:
+    return int(lib().mudiff_launch_count())

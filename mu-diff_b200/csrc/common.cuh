@@ -1,0 +1,76 @@
+// Shared helpers for libmudiff_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/mudiff_b200.h"
+
+#define MUDIFF_NUM_SMS 148
+
+extern int64_t g_mudiff_launches;   // defined in abi.cu
+
+static inline int mudiff_launch_status() {
+  ++g_mudiff_launches;
+  cudaError_t e = cudaPeekAtLastError();   // do not clear sticky state of other libs
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  return 0;
+}
+
+// ---- storage <-> fp32 -----------------------------------------------------------
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+  static __device__ __forceinline__ float to_f(float v) { return v; }
+  static __device__ __forceinline__ float from_f(float v) { return v; }
+};
+template <> struct Cvt<__nv_bfloat16> {
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+template <> struct Cvt<__half> {
+  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+
+// A 16-byte vector of T viewed as floats.
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T>
+__device__ __forceinline__ void load_vec(const T* p, float (&v)[16 / sizeof(T)]) {
+  constexpr int N = 16 / sizeof(T);
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = Cvt<T>::to_f(e[i]);
+}
+template <typename T>
+__device__ __forceinline__ void store_vec(T* p, const float (&v)[16 / sizeof(T)]) {
+  constexpr int N = 16 / sizeof(T);
+  uint4 raw;
+  T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = Cvt<T>::from_f(v[i]);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// exact-ish variants for the fp32 parity path
+__device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_exact(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case MUDIFF_ACT_SILU: return silu_exact(v);
+    case MUDIFF_ACT_SIGMOID: return sigmoid_exact(v);
+    case MUDIFF_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+static inline int grid_for(int64_t work, int block, int max_blocks = MUDIFF_NUM_SMS * 16) {
+  int64_t g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}

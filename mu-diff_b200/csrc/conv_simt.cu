@@ -1,0 +1,268 @@
+// CUDA-core implicit-GEMM convolution / contraction on NHWC tensors (fp32 math).
+// This is (1) the fp32 parity path (max-abs <= 1e-4 vs the fp32 reference needs true
+// fp32 products, which tcgen05 does not offer), and (2) the path for shapes the
+// tensor-core kernel does not take: Cin=1 stem convs, the Cout=1 head conv, the
+// stride-2 input-pyramid conv.  Same mudiff_conv_desc contract as mudiff_conv_tc.
+#include "common.cuh"
+
+namespace {
+
+struct SimtP {
+  const void* a[3];
+  int a_c[3], a_ld[3], a_taps[3], a_koff[3];
+  int nseg, a_batched;
+  int batch, h, w, ho, wo, stride, pad;
+  const void* wt; int64_t w_bstride; int ktot; int w_ld;
+  int n;
+  const float* bias; const float* rowbias; int rowbias_ld;
+  const void* residual; int res_ld;
+  float alpha, beta; int act;
+  void* out; int out_ld, out_coff;
+};
+
+template <typename TO>
+__device__ __forceinline__ void epilogue_store(const SimtP& p, int b, int64_t pix, int n, float acc) {
+  float v = acc;
+  if (p.bias) v += p.bias[n];
+  if (p.rowbias) v += p.rowbias[(int64_t)b * p.rowbias_ld + n];
+  v *= p.alpha;
+  if (p.residual) v = fmaf(p.beta, Cvt<TO>::to_f(((const TO*)p.residual)[pix * p.res_ld + n]), v);
+  v = apply_act(v, p.act);
+  ((TO*)p.out)[pix * p.out_ld + p.out_coff + n] = Cvt<TO>::from_f(v);
+}
+
+// ---------------------------------------------------------------------------------
+// generic tile kernel: 64 pixels x 64 channels per block, 256 threads, 4x4 per thread
+// ---------------------------------------------------------------------------------
+#define BM 64
+#define BN 64
+#define BK 16
+template <typename TA, typename TO>
+__global__ void __launch_bounds__(256) conv_simt_kernel(SimtP p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  __shared__ int s_oy[BM], s_ox[BM];
+  const int b = blockIdx.z;
+  const int hw_o = p.ho * p.wo;
+  const int pix0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int tid = threadIdx.x;
+  if (tid < BM) {
+    int pp = pix0 + tid;
+    s_oy[tid] = pp < hw_o ? pp / p.wo : -100000;
+    s_ox[tid] = pp < hw_o ? pp % p.wo : 0;
+  }
+  __syncthreads();
+  const TA* wbase = (const TA*)p.wt + (int64_t)b * p.w_bstride;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int tx = tid % 16, ty = tid / 16;      // tx -> 4 channels, ty -> 4 pixels
+  const int lp = tid / 4, lk = (tid % 4) * 4;  // loader: pixel / weight-row lp, 4 consecutive k
+  for (int s = 0; s < p.nseg; ++s) {
+    const TA* abase = (const TA*)p.a[s] + (p.a_batched ? (int64_t)b * p.h * p.w * p.a_ld[s] : 0);
+    const int C = p.a_c[s];
+    for (int tap = 0; tap < p.a_taps[s]; ++tap) {
+      const int dy = p.a_taps[s] == 9 ? tap / 3 - p.pad : 0;
+      const int dx = p.a_taps[s] == 9 ? tap % 3 - p.pad : 0;
+      const int iy = s_oy[lp] * p.stride + dy, ix = s_ox[lp] * p.stride + dx;
+      const bool inb = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+      const TA* arow = abase + ((int64_t)iy * p.w + ix) * p.a_ld[s];
+      for (int c0 = 0; c0 < C; c0 += BK) {
+        // A tile: 64 pixels x 16 channels
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int c = c0 + lk + i;
+          As[lk + i][lp] = (inb && c < C) ? Cvt<TA>::to_f(arow[c]) : 0.f;
+        }
+        // W tile: 64 out-channels x 16 k
+        {
+          int n = n0 + lp;
+          const TA* wrow = wbase + (int64_t)n * p.w_ld + p.a_koff[s] + tap * C + c0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int c = c0 + lk + i;
+            Ws[lk + i][lp] = (n < p.n && c < C) ? Cvt<TA>::to_f(wrow[lk + i]) : 0.f;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+          float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+          float4 wv = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+          float a4[4] = {av.x, av.y, av.z, av.w};
+          float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], w4[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int pp = pix0 + ty * 4 + i;
+    if (pp >= hw_o) continue;
+    int64_t pix = (int64_t)b * hw_o + pp;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < p.n) epilogue_store<TO>(p, b, pix, n, acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// small-N kernel (N <= 4, e.g. the 64->1 head conv): 8 lanes per output pixel, each
+// lane owns one 8-channel slice of every 64-channel block, shuffle-reduce at the end.
+// Weights staged in shared memory as fp32.
+// ---------------------------------------------------------------------------------
+template <typename TA, typename TO>
+__global__ void __launch_bounds__(256) conv_small_n_kernel(SimtP p) {
+  extern __shared__ float sw[];                 // [n][ktot]
+  for (int i = threadIdx.x; i < p.n * p.ktot; i += blockDim.x) sw[i] = Cvt<TA>::to_f(((const TA*)p.wt)[i]);
+  __syncthreads();
+  const int hw_o = p.ho * p.wo;
+  const int64_t total = (int64_t)p.batch * hw_o;
+  const int sub = threadIdx.x & 7;
+  for (int64_t pix = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; pix < total;
+       pix += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    const int b = (int)(pix / hw_o);
+    const int pp = (int)(pix % hw_o);
+    const int oy = pp / p.wo, ox = pp % p.wo;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < p.nseg; ++s) {
+      const TA* abase = (const TA*)p.a[s] + (int64_t)b * p.h * p.w * p.a_ld[s];
+      const int C = p.a_c[s];
+      for (int tap = 0; tap < p.a_taps[s]; ++tap) {
+        const int dy = p.a_taps[s] == 9 ? tap / 3 - p.pad : 0;
+        const int dx = p.a_taps[s] == 9 ? tap % 3 - p.pad : 0;
+        const int iy = oy * p.stride + dy, ix = ox * p.stride + dx;
+        if (iy < 0 || iy >= p.h || ix < 0 || ix >= p.w) continue;
+        const TA* arow = abase + ((int64_t)iy * p.w + ix) * p.a_ld[s];
+        const int kb = p.a_koff[s] + tap * C;
+        for (int c = sub; c < C; c += 8) {
+          float av = Cvt<TA>::to_f(arow[c]);
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+            if (n < p.n) acc[n] = fmaf(av, sw[n * p.ktot + kb + c], acc[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 1);
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 2);
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 4);
+    }
+    if (sub == 0)
+      for (int n = 0; n < p.n; ++n) epilogue_store<TO>(p, b, pix, n, acc[n]);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// small-K kernel (Ktot <= 36, e.g. the 1->64 stem convs): one thread per (pixel, 8 output
+// channels); input taps gathered once per pixel, weights in shared memory.
+// ---------------------------------------------------------------------------------
+template <typename TA, typename TO>
+__global__ void __launch_bounds__(256) conv_small_k_kernel(SimtP p) {
+  extern __shared__ float sw[];                 // [ktot][n]  (n innermost)
+  for (int i = threadIdx.x; i < p.n * p.ktot; i += blockDim.x) {
+    int n = i / p.ktot, k = i % p.ktot;
+    sw[k * p.n + n] = Cvt<TA>::to_f(((const TA*)p.wt)[i]);
+  }
+  __syncthreads();
+  const int hw_o = p.ho * p.wo;
+  const int nv = p.n / 8;
+  const int64_t total = (int64_t)p.batch * hw_o * nv;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = idx / nv;
+    const int n0 = (int)(idx % nv) * 8;
+    const int b = (int)(pix / hw_o);
+    const int pp = (int)(pix % hw_o);
+    const int oy = pp / p.wo, ox = pp % p.wo;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int s = 0; s < p.nseg; ++s) {
+      const TA* abase = (const TA*)p.a[s] + (int64_t)b * p.h * p.w * p.a_ld[s];
+      const int C = p.a_c[s];
+      for (int tap = 0; tap < p.a_taps[s]; ++tap) {
+        const int dy = p.a_taps[s] == 9 ? tap / 3 - p.pad : 0;
+        const int dx = p.a_taps[s] == 9 ? tap % 3 - p.pad : 0;
+        const int iy = oy * p.stride + dy, ix = ox * p.stride + dx;
+        if (iy < 0 || iy >= p.h || ix < 0 || ix >= p.w) continue;
+        const TA* arow = abase + ((int64_t)iy * p.w + ix) * p.a_ld[s];
+        for (int c = 0; c < C; ++c) {
+          float av = Cvt<TA>::to_f(arow[c]);
+          const float* wr = sw + (p.a_koff[s] + tap * C + c) * p.n + n0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(av, wr[j], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) epilogue_store<TO>(p, b, pix, n0 + j, acc[j]);
+  }
+}
+
+template <typename TA, typename TO>
+int launch_simt(const SimtP& p, cudaStream_t st) {
+  const int hw_o = p.ho * p.wo;
+  const bool plain = p.a_batched && p.w_bstride == 0 && p.w_ld == p.ktot;
+  if (plain && p.n <= 4 && (size_t)p.n * p.ktot * 4 <= 48 * 1024) {
+    int64_t threads = (int64_t)p.batch * hw_o * 8;
+    conv_small_n_kernel<TA, TO><<<grid_for(threads, 256), 256, sizeof(float) * p.n * p.ktot, st>>>(p);
+    return mudiff_launch_status();
+  }
+  if (plain && p.ktot <= 36 && p.n % 8 == 0 && (size_t)p.n * p.ktot * 4 <= 48 * 1024) {
+    int64_t threads = (int64_t)p.batch * hw_o * (p.n / 8);
+    conv_small_k_kernel<TA, TO><<<grid_for(threads, 256), 256, sizeof(float) * p.n * p.ktot, st>>>(p);
+    return mudiff_launch_status();
+  }
+  if (p.batch > 65535) return MUDIFF_EUNSUPPORTED;
+  dim3 grid((hw_o + BM - 1) / BM, (p.n + BN - 1) / BN, p.batch);
+  conv_simt_kernel<TA, TO><<<grid, 256, 0, st>>>(p);
+  return mudiff_launch_status();
+}
+
+}  // namespace
+
+extern "C" int mudiff_conv_simt(const mudiff_conv_desc* d, int dtype, void* stream) {
+  if (!d || d->nseg < 1 || d->nseg > 3 || d->batch <= 0 || d->h <= 0 || d->w <= 0 || d->n <= 0) return MUDIFF_EINVAL;
+  if (d->stride != 1 && d->stride != 2) return MUDIFF_EINVAL;
+  if (!d->wt || !d->out) return MUDIFF_EINVAL;
+  if (d->stats) return MUDIFF_EUNSUPPORTED;
+  SimtP p;
+  int koff = 0;
+  bool any9 = false;
+  for (int s = 0; s < 3; ++s) {
+    if (s < d->nseg) {
+      if (!d->a[s] || d->a_c[s] <= 0 || (d->a_taps[s] != 1 && d->a_taps[s] != 9)) return MUDIFF_EINVAL;
+      p.a[s] = d->a[s]; p.a_c[s] = d->a_c[s]; p.a_ld[s] = d->a_ld[s]; p.a_taps[s] = d->a_taps[s]; p.a_koff[s] = koff;
+      koff += d->a_taps[s] * d->a_c[s];
+      any9 |= d->a_taps[s] == 9;
+    } else { p.a[s] = nullptr; p.a_c[s] = 0; p.a_ld[s] = 0; p.a_taps[s] = 0; p.a_koff[s] = 0; }
+  }
+  p.nseg = d->nseg; p.a_batched = d->a_batched;
+  p.batch = d->batch; p.h = d->h; p.w = d->w; p.stride = d->stride; p.pad = d->pad;
+  if (d->stride == 1) { p.ho = d->h; p.wo = d->w; if (any9 && d->pad != 1) return MUDIFF_EUNSUPPORTED; }
+  else {
+    int k = any9 ? 3 : 1;
+    p.ho = (d->h + 2 * d->pad - k) / 2 + 1; p.wo = (d->w + 2 * d->pad - k) / 2 + 1;
+  }
+  p.wt = d->wt; p.w_bstride = d->w_bstride; p.ktot = koff; p.w_ld = d->w_ld > 0 ? d->w_ld : koff; p.n = d->n;
+  p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
+  p.residual = d->residual; p.res_ld = d->res_ld; p.alpha = d->alpha; p.beta = d->beta; p.act = d->act;
+  p.out = d->out; p.out_ld = d->out_ld; p.out_coff = d->out_coff;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MUDIFF_F32 && d->out_dtype == MUDIFF_F32) return launch_simt<float, float>(p, st);
+  if (dtype == MUDIFF_F32 && d->out_dtype == MUDIFF_BF16) return launch_simt<float, __nv_bfloat16>(p, st);
+  if (dtype == MUDIFF_BF16 && d->out_dtype == MUDIFF_BF16) return launch_simt<__nv_bfloat16, __nv_bfloat16>(p, st);
+  if (dtype == MUDIFF_BF16 && d->out_dtype == MUDIFF_F32) return launch_simt<__nv_bfloat16, float>(p, st);
+  return MUDIFF_EUNSUPPORTED;
+}

@@ -1,0 +1,182 @@
+// GroupNorm statistics + (AdaGN scale/shift) + activation on NHWC tensors, with the
+// channel-concat of two sources folded in (no materialised torch.cat).
+//   stats : per (batch, group) (sum, sumsq) in fp64, block-partial -> atomicAdd(double)
+//   apply : y = act(x * scale[b,c] + shift[b,c]),  scale = gamma*rstd, shift = beta - mean*scale
+// HBM-bound: stats reads the tensor once, apply reads once + writes once, 16-byte vectors.
+#include "common.cuh"
+
+namespace {
+
+#define GN_MAX_C 1024
+
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const T* __restrict__ x1, int c1, int ld1,
+                                int64_t hw, int groups, double* __restrict__ stats, int pix_per_block) {
+  constexpr int V = 16 / sizeof(T);
+  const int C = c0 + c1;
+  const int cv = C / V;
+  const int b = blockIdx.y;
+  __shared__ float s_sum[GN_MAX_C];
+  __shared__ float s_sq[GN_MAX_C];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+  __syncthreads();
+  // blockDim.x is a multiple of cv: each thread keeps one channel vector for the whole loop
+  const int my_cv = threadIdx.x % cv;
+  const int lane = threadIdx.x / cv;
+  const int lanes = blockDim.x / cv;
+  const int ch = my_cv * V;
+  const T* base; int ld; int cc;
+  if (ch < c0) { base = x0 + (int64_t)b * hw * ld0; ld = ld0; cc = ch; }
+  else { base = x1 + (int64_t)b * hw * ld1; ld = ld1; cc = ch - c0; }
+  float sum[V], sq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { sum[i] = 0.f; sq[i] = 0.f; }
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  int64_t p1 = p0 + pix_per_block; if (p1 > hw) p1 = hw;
+  for (int64_t p = p0 + lane; p < p1; p += lanes) {
+    float v[V];
+    load_vec<T>(base + p * ld + cc, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { sum[i] += v[i]; sq[i] = fmaf(v[i], v[i], sq[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) { atomicAdd(&s_sum[ch + i], sum[i]); atomicAdd(&s_sq[ch + i], sq[i]); }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double a = 0.0, q = 0.0;
+    for (int i = 0; i < cpg; ++i) { a += (double)s_sum[g * cpg + i]; q += (double)s_sq[g * cpg + i]; }
+    atomicAdd(&stats[((int64_t)b * groups + g) * 2 + 0], a);
+    atomicAdd(&stats[((int64_t)b * groups + g) * 2 + 1], q);
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void gn_apply_kernel(const TI* __restrict__ x0, int c0, int ld0, const TI* __restrict__ x1, int c1, int ld1,
+                                const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int64_t gb_bstride, TO* __restrict__ out, int ld_out,
+                                int64_t hw, int groups, float eps, int act, int pix_per_block) {
+  // vector width is chosen on the WIDER of the two element types so both sides stay 16-byte (or less) aligned
+  constexpr int V = (sizeof(TI) >= sizeof(TO)) ? 16 / sizeof(TI) : 16 / sizeof(TO);
+  const int C = c0 + c1;
+  const int cv = C / V;
+  const int b = blockIdx.y;
+  __shared__ float s_scale[GN_MAX_C];
+  __shared__ float s_shift[GN_MAX_C];
+  const int cpg = C / groups;
+  const double cnt = (double)hw * (double)cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    double m = stats[((int64_t)b * groups + g) * 2 + 0] / cnt;
+    double var = stats[((int64_t)b * groups + g) * 2 + 1] / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float ga = gamma ? gamma[(int64_t)b * gb_bstride + c] : 1.f;
+    float be = beta ? beta[(int64_t)b * gb_bstride + c] : 0.f;
+    float sc = ga * rstd;
+    s_scale[c] = sc;
+    s_shift[c] = be - (float)m * sc;
+  }
+  __syncthreads();
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  int64_t p1 = p0 + pix_per_block; if (p1 > hw) p1 = hw;
+  const int64_t total = (p1 - p0) * cv;
+  const TI* b0 = x0 + (int64_t)b * hw * ld0;
+  const TI* b1 = x1 ? x1 + (int64_t)b * hw * ld1 : nullptr;
+  TO* ob = out + (int64_t)b * hw * ld_out;
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const int64_t p = p0 + i / cv;
+    const int ch = (int)(i % cv) * V;
+    const TI* src = ch < c0 ? b0 + p * ld0 + ch : b1 + p * ld1 + (ch - c0);
+    float v[V];
+    if constexpr (V * sizeof(TI) == 16) {
+      load_vec<TI>(src, *reinterpret_cast<float(*)[16 / sizeof(TI)]>(v));
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = Cvt<TI>::to_f(src[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float t = fmaf(v[k], s_scale[ch + k], s_shift[ch + k]);
+      v[k] = act == MUDIFF_ACT_SILU ? silu_exact(t) : t;
+    }
+    TO* dst = ob + p * ld_out + ch;
+    if constexpr (V * sizeof(TO) == 16) {
+      store_vec<TO>(dst, *reinterpret_cast<float(*)[16 / sizeof(TO)]>(v));
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) dst[k] = Cvt<TO>::from_f(v[k]);
+    }
+  }
+}
+
+template <typename T>
+int launch_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int batch, int64_t hw,
+                 int groups, double* stats, cudaStream_t st) {
+  constexpr int V = 16 / sizeof(T);
+  const int C = c0 + c1;
+  if (C % V || c0 % V || ld0 % V || (x1 && ld1 % V) || C > GN_MAX_C || C % groups) return MUDIFF_EUNSUPPORTED;
+  if (((uintptr_t)x0 % 16) || (x1 && ((uintptr_t)x1 % 16))) return MUDIFF_EUNSUPPORTED;
+  const int cv = C / V;
+  int block = (256 / cv) * cv;
+  if (block < cv) block = cv;                // cv <= 256 since C <= 1024, V >= 4
+  // enough blocks to fill the machine ~4x, at least 64 pixels per lane-iteration set
+  int64_t want = (int64_t)MUDIFF_NUM_SMS * 8 / (batch > 0 ? batch : 1);
+  if (want < 1) want = 1;
+  int64_t ppb = (hw + want - 1) / want;
+  if (ppb < 256) ppb = 256;
+  int chunks = (int)((hw + ppb - 1) / ppb);
+  dim3 grid(chunks, batch);
+  gn_stats_kernel<T><<<grid, block, 0, st>>>((const T*)x0, c0, ld0, (const T*)x1, c1, ld1, hw, groups, stats, (int)ppb);
+  return mudiff_launch_status();
+}
+
+template <typename TI, typename TO>
+int launch_apply(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, const double* stats,
+                 const float* gamma, const float* beta, int64_t gbs, void* out, int ld_out, int batch, int64_t hw,
+                 int groups, float eps, int act, cudaStream_t st) {
+  constexpr int V = (sizeof(TI) >= sizeof(TO)) ? 16 / sizeof(TI) : 16 / sizeof(TO);
+  const int C = c0 + c1;
+  if (C % V || c0 % V || ld0 % V || (x1 && ld1 % V) || ld_out % V || C > GN_MAX_C || C % groups) return MUDIFF_EUNSUPPORTED;
+  if (((uintptr_t)x0 % 16) || (x1 && ((uintptr_t)x1 % 16)) || ((uintptr_t)out % 16)) return MUDIFF_EUNSUPPORTED;
+  int64_t want = (int64_t)MUDIFF_NUM_SMS * 8 / (batch > 0 ? batch : 1);
+  if (want < 1) want = 1;
+  int64_t ppb = (hw + want - 1) / want;
+  if (ppb < 128) ppb = 128;
+  int chunks = (int)((hw + ppb - 1) / ppb);
+  dim3 grid(chunks, batch);
+  gn_apply_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)x0, c0, ld0, (const TI*)x1, c1, ld1, stats, gamma, beta, gbs,
+                                                (TO*)out, ld_out, hw, groups, eps, act, (int)ppb);
+  return mudiff_launch_status();
+}
+
+}  // namespace
+
+extern "C" int mudiff_gn_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int dtype,
+                               int batch, int64_t hw, int groups, double* stats, void* stream) {
+  if (batch <= 0 || hw <= 0 || groups <= 0 || c0 <= 0 || c1 < 0 || !x0 || !stats) return MUDIFF_EINVAL;
+  if (!x1) c1 = 0;
+  if (batch > 65535) return MUDIFF_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MUDIFF_F32) return launch_stats<float>(x0, c0, ld0, x1, c1, ld1, batch, hw, groups, stats, st);
+  if (dtype == MUDIFF_BF16) return launch_stats<__nv_bfloat16>(x0, c0, ld0, x1, c1, ld1, batch, hw, groups, stats, st);
+  return MUDIFF_EUNSUPPORTED;
+}
+
+extern "C" int mudiff_gn_apply(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int dtype_in,
+                               const double* stats, const float* gamma, const float* beta, int64_t gb_bstride,
+                               void* out, int ld_out, int dtype_out, int batch, int64_t hw, int groups,
+                               float eps, int act, void* stream) {
+  if (batch <= 0 || hw <= 0 || groups <= 0 || c0 <= 0 || c1 < 0 || !x0 || !stats || !out) return MUDIFF_EINVAL;
+  if (act != MUDIFF_ACT_NONE && act != MUDIFF_ACT_SILU) return MUDIFF_EINVAL;
+  if (!x1) c1 = 0;
+  if (batch > 65535) return MUDIFF_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+#define AP(TI, TO) return launch_apply<TI, TO>(x0, c0, ld0, x1, c1, ld1, stats, gamma, beta, gb_bstride, out, ld_out, batch, hw, groups, eps, act, st)
+  if (dtype_in == MUDIFF_F32 && dtype_out == MUDIFF_F32) AP(float, float);
+  if (dtype_in == MUDIFF_BF16 && dtype_out == MUDIFF_BF16) AP(__nv_bfloat16, __nv_bfloat16);
+  if (dtype_in == MUDIFF_F32 && dtype_out == MUDIFF_BF16) AP(float, __nv_bfloat16);
+  if (dtype_in == MUDIFF_BF16 && dtype_out == MUDIFF_F32) AP(__nv_bfloat16, float);
+#undef AP
+  return MUDIFF_EUNSUPPORTED;
+}

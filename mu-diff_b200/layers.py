@@ -1,0 +1,131 @@
+"""DDPM-era primitives on the hot path (backbones/layers.py): default_init (:92-95),
+ddpm_conv1x1 / ddpm_conv3x3 factories (:104-129), get_timestep_embedding (:465-479),
+NIN (:496-505).  Convs are `Conv2d` modules with nn.Conv2d-compatible parameters
+(`weight [Cout,Cin,k,k]`, `bias [Cout]`) whose forward runs the libmudiff_b200 kernels."""
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+
+
+def variance_scaling(scale, mode, distribution, in_axis=1, out_axis=0, dtype=torch.float32, device='cpu'):
+    """JAX-style variance scaling initialiser (backbones/layers.py:58-89)."""
+
+    def init(shape, dtype=dtype, device=device):
+        rf = np.prod(shape) / shape[in_axis] / shape[out_axis]
+        fan_in, fan_out = shape[in_axis] * rf, shape[out_axis] * rf
+        denom = {'fan_in': fan_in, 'fan_out': fan_out, 'fan_avg': (fan_in + fan_out) / 2}.get(mode)
+        if denom is None:
+            raise ValueError("invalid mode for variance scaling initializer: {}".format(mode))
+        var = scale / denom
+        if distribution == 'normal':
+            return torch.randn(*shape, dtype=dtype, device=device) * np.sqrt(var)
+        if distribution == 'uniform':
+            return (torch.rand(*shape, dtype=dtype, device=device) * 2. - 1.) * np.sqrt(3 * var)
+        raise ValueError("invalid distribution for variance scaling initializer")
+
+    return init
+
+
+def default_init(scale=1.):
+    scale = 1e-10 if scale == 0 else scale
+    return variance_scaling(scale, 'fan_avg', 'uniform')
+
+
+class PackCache:
+    """Caches kernel-ready (packed / cast) copies of parameters; invalidated when a
+    parameter is modified in place (load_state_dict bumps `_version`) or replaced."""
+
+    def _packed(self, key, params, builder):
+        cache = self.__dict__.setdefault('_pack_cache', {})
+        sig = tuple((p.data_ptr(), p._version, p.device, p.dtype) for p in params)
+        hit = cache.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        with torch.no_grad():
+            val = builder()
+        cache[key] = (sig, val)
+        return val
+
+
+class Conv2d(nn.Module, PackCache):
+    """3x3 (pad 1) or 1x1 convolution, stride 1, NCHW-logical in/out, channels-last memory."""
+
+    def __init__(self, in_planes, out_planes, kernel_size, init_scale=1., bias=True, stride=1, padding=None):
+        super().__init__()
+        assert kernel_size in (1, 3)
+        self.in_channels, self.out_channels, self.kernel_size = in_planes, out_planes, kernel_size
+        self.stride = stride
+        self.padding = kernel_size // 2 if padding is None else padding
+        self.weight = nn.Parameter(default_init(init_scale)((out_planes, in_planes, kernel_size, kernel_size)))
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_planes))
+        else:
+            self.register_parameter('bias', None)
+
+    def packed_weight(self, dtype, seg_channels=None):
+        seg = tuple(seg_channels) if seg_channels else (self.in_channels,)
+        return self._packed(('w', dtype, seg), [self.weight],
+                            lambda: ops.pack_conv_weight(self.weight, seg, dtype))
+
+    def bias_f32(self):
+        if self.bias is None:
+            return None
+        return self._packed(('b',), [self.bias], lambda: self.bias.detach().float().contiguous())
+
+    def forward(self, x, *, compute_dtype=None, **kw):
+        L.require_cuda(x)
+        if self.stride != 1 or self.padding != self.kernel_size // 2:
+            raise RuntimeError("mu-diff_b200 Conv2d: only stride 1 'same' convolutions are on the path")
+        dt = compute_dtype or (x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
+        if self.in_channels < 8:          # stem: keep the 1-channel input in fp32
+            xin = ops.as_nhwc(x, torch.float32)
+            wt = self.packed_weight(torch.float32)
+        else:
+            xin = ops.as_nhwc(x, dt)
+            wt = self.packed_weight(dt)
+        taps = 9 if self.kernel_size == 3 else 1
+        return ops.conv([(xin, taps)], wt, self.out_channels, bias=self.bias_f32(), pad=self.padding,
+                        out_dtype=kw.pop('out_dtype', dt), **kw)
+
+
+def ddpm_conv1x1(in_planes, out_planes, stride=1, bias=True, init_scale=1., padding=0):
+    """backbones/layers.py:104-109"""
+    return Conv2d(in_planes, out_planes, 1, init_scale=init_scale, bias=bias, stride=stride, padding=padding)
+
+
+def ddpm_conv3x3(in_planes, out_planes, stride=1, bias=True, dilation=1, init_scale=1., padding=1):
+    """backbones/layers.py:122-129"""
+    assert dilation == 1
+    return Conv2d(in_planes, out_planes, 3, init_scale=init_scale, bias=bias, stride=stride, padding=padding)
+
+
+def get_timestep_embedding(timesteps, embedding_dim, max_positions=10000):
+    """backbones/layers.py:465-479 (sinusoidal embedding of the integer step index)."""
+    assert len(timesteps.shape) == 1
+    return ops.timestep_embedding(timesteps, embedding_dim, float(max_positions))
+
+
+class NIN(nn.Module, PackCache):
+    """backbones/layers.py:496-505: y = x . W + b over the channel axis (a 1x1 conv with W [in, out])."""
+
+    def __init__(self, in_dim, num_units, init_scale=0.1):
+        super().__init__()
+        self.W = nn.Parameter(default_init(scale=init_scale)((in_dim, num_units)), requires_grad=True)
+        self.b = nn.Parameter(torch.zeros(num_units), requires_grad=True)
+
+    def packed_weight(self, dtype):
+        return self._packed(('w', dtype), [self.W], lambda: self.W.detach().t().to(dtype).contiguous())
+
+    def bias_f32(self):
+        return self._packed(('b',), [self.b], lambda: self.b.detach().float().contiguous())
+
+    def forward(self, x, **kw):
+        L.require_cuda(x)
+        dt = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        x = ops.as_nhwc(x, dt)
+        return ops.conv([(x, 1)], self.packed_weight(dt), self.W.shape[1], bias=self.bias_f32(), pad=0, **kw)

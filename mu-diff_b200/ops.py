@@ -1,0 +1,372 @@
+"""Functional wrappers: torch tensors in, torch tensors out, CUDA work done by libmudiff_b200.
+
+Layout contract: 4-D activations are logical NCHW tensors whose memory is channels-last
+(NHWC), i.e. `x.permute(0, 2, 3, 1)` is contiguous.  `as_nhwc()` converts anything else
+at the API boundary.  PyTorch is used for allocation, streams and views only.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+SQRT2_INV = 1.0 / math.sqrt(2.0)
+
+
+# ---------------------------------------------------------------------------------
+# layout helpers
+# ---------------------------------------------------------------------------------
+def is_nhwc_view(x: torch.Tensor) -> bool:
+    """True if x (logical [B,C,H,W]) is channels-last memory, possibly a channel-slice of a wider
+    channels-last tensor (pixel stride ld >= C)."""
+    b, c, h, w = x.shape
+    if c > 1 and x.stride(1) != 1:
+        return False
+    if w > 1:
+        ld = x.stride(3)
+    elif h > 1:
+        ld = x.stride(2)
+    elif b > 1:
+        ld = x.stride(0)
+    else:
+        return True
+    if ld < c:
+        return False
+    if h > 1 and x.stride(2) != w * ld:
+        return False
+    if b > 1 and x.stride(0) != h * w * ld:
+        return False
+    return True
+
+
+def as_nhwc(x: torch.Tensor, dtype=None) -> torch.Tensor:
+    """Return x (logical [B,C,H,W]) with channels-last memory and optional dtype."""
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    if is_nhwc_view(x):
+        return x
+    return x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+def empty_nhwc(b, c, h, w, dtype, device) -> torch.Tensor:
+    return torch.empty((b, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def _pix_ld(x):
+    """pixel stride (elements) of a channels-last tensor or channel-slice view of one."""
+    b, c, h, w = x.shape
+    if w > 1:
+        return x.stride(3)
+    if h > 1:
+        return x.stride(2)
+    if b > 1:
+        return x.stride(0)
+    return c
+
+
+def channel_slice(x: torch.Tensor, c0: int, c1: int) -> torch.Tensor:
+    return x[:, c0:c1]
+
+
+# ---------------------------------------------------------------------------------
+# FIR / bias-act (the reference's native ops)
+# ---------------------------------------------------------------------------------
+_kernel_cache = {}
+
+
+def fir_kernel_device(k_np, device) -> torch.Tensor:
+    """fp32 device copy of a (small) FIR kernel, cached so that no H2D copy happens per call
+    (the reference rebuilds torch.tensor(k, device=...) on every call,
+    up_or_down_sampling.py:145,181,228,261, which is not graph-capture safe)."""
+    key = (k_np.tobytes(), k_np.shape, str(device))
+    t = _kernel_cache.get(key)
+    if t is None:
+        t = torch.tensor(k_np, dtype=torch.float32, device=device)
+        _kernel_cache[key] = t
+    return t
+
+
+def upfirdn2d_raw(x, kernel_f32, major, in_h, in_w, minor, up, down, pad, out):
+    """x/out are flat device buffers in [major,H,W,minor] order."""
+    kh, kw = kernel_f32.shape
+    rc = L.lib().mudiff_upfirdn2d(x.data_ptr(), out.data_ptr(), kernel_f32.data_ptr(), L.dtype_code(x.dtype),
+                                  major, in_h, in_w, minor, kh, kw, up[0], up[1], down[0], down[1],
+                                  pad[0], pad[1], pad[2], pad[3], L.stream_ptr(x.device))
+    L.check(rc, 'upfirdn2d')
+
+
+def upfirdn2d_nhwc(x, kernel_f32, up=1, down=1, pad=(0, 0)):
+    """FIR on a channels-last activation (all channels share the kernel)."""
+    L.require_cuda(x, kernel_f32)
+    b, c, h, w = x.shape
+    x = as_nhwc(x)
+    kh, kw = kernel_f32.shape
+    oh = (h * up + pad[0] + pad[1] - kh) // down + 1
+    ow = (w * up + pad[0] + pad[1] - kw) // down + 1
+    out = empty_nhwc(b, c, oh, ow, x.dtype, x.device)
+    if _pix_ld(x) != c:
+        x = as_nhwc(x.contiguous(memory_format=torch.channels_last))
+    upfirdn2d_raw(x, kernel_f32, b, h, w, c, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]), out)
+    return out
+
+
+# ---------------------------------------------------------------------------------
+# GroupNorm
+# ---------------------------------------------------------------------------------
+def gn_stats(srcs, groups):
+    """srcs: 1 or 2 channels-last tensors (channel concat). returns double [B,G,2]."""
+    x0 = srcs[0]
+    x1 = srcs[1] if len(srcs) > 1 else None
+    b, c0, h, w = x0.shape
+    stats = torch.zeros((b, groups, 2), dtype=torch.float64, device=x0.device)
+    rc = L.lib().mudiff_gn_stats(x0.data_ptr(), c0, _pix_ld(x0),
+                                 x1.data_ptr() if x1 is not None else None,
+                                 x1.shape[1] if x1 is not None else 0, _pix_ld(x1) if x1 is not None else 0,
+                                 L.dtype_code(x0.dtype), b, h * w, groups, stats.data_ptr(), L.stream_ptr(x0.device))
+    L.check(rc, 'gn_stats')
+    return stats
+
+
+def gn_apply(srcs, stats, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_NONE,
+             out_dtype=None, out=None):
+    x0 = srcs[0]
+    x1 = srcs[1] if len(srcs) > 1 else None
+    b, c0, h, w = x0.shape
+    c = c0 + (x1.shape[1] if x1 is not None else 0)
+    out_dtype = out_dtype or x0.dtype
+    if out is None:
+        out = empty_nhwc(b, c, h, w, out_dtype, x0.device)
+    rc = L.lib().mudiff_gn_apply(x0.data_ptr(), c0, _pix_ld(x0),
+                                 x1.data_ptr() if x1 is not None else None,
+                                 x1.shape[1] if x1 is not None else 0, _pix_ld(x1) if x1 is not None else 0,
+                                 L.dtype_code(x0.dtype), stats.data_ptr(),
+                                 gamma.data_ptr() if gamma is not None else None,
+                                 beta.data_ptr() if beta is not None else None, gb_bstride,
+                                 out.data_ptr(), _pix_ld(out), L.dtype_code(out.dtype), b, h * w, groups,
+                                 float(eps), act, L.stream_ptr(x0.device))
+    L.check(rc, 'gn_apply')
+    return out
+
+
+def group_norm(srcs, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_NONE, out_dtype=None):
+    srcs = [as_nhwc(s) for s in srcs]
+    return gn_apply(srcs, gn_stats(srcs, groups), groups, gamma, beta, gb_bstride, eps, act, out_dtype)
+
+
+# ---------------------------------------------------------------------------------
+# convolution / contraction
+# ---------------------------------------------------------------------------------
+def pack_conv_weight(weight: torch.Tensor, seg_channels, dtype) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] -> [Cout, sum_seg kh*kw*C_seg] with k = seg_off + tap*C_seg + c."""
+    parts, off = [], 0
+    cout = weight.shape[0]
+    for cs in seg_channels:
+        parts.append(weight[:, off:off + cs].permute(0, 2, 3, 1).reshape(cout, -1))
+        off += cs
+    assert off == weight.shape[1], (off, weight.shape)
+    return torch.cat(parts, dim=1).to(dtype).contiguous()
+
+
+def tc_eligible(segs, n, stride, dtype) -> bool:
+    if dtype != torch.bfloat16 or stride != 1 or n % 32:
+        return False
+    return all(s.shape[1] % 64 == 0 for s, _ in segs)
+
+
+def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta=0.0, act=L.ACT_NONE,
+         out=None, out_coff=0, out_dtype=None, stride=1, pad=1, w_bstride=0, w_ld=0, a_batched=True,
+         batch=None, flags=0, force=None):
+    """Implicit-GEMM convolution.  segs = [(tensor NCHW-logical/channels-last, taps)], wt packed K-major.
+    Chooses the tcgen05 kernel when eligible (bf16, Cin % 64 == 0, N % 32 == 0, stride 1), otherwise the
+    CUDA-core kernel.  `force` in {None,'tc','simt'}."""
+    x0 = segs[0][0]
+    dev = x0.device
+    b = batch if batch is not None else x0.shape[0]
+    h, w = x0.shape[2], x0.shape[3]
+    if stride == 1:
+        ho, wo = h, w
+    else:
+        k = 3 if any(t == 9 for _, t in segs) else 1
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    out_dtype = out_dtype or x0.dtype
+    if out is None:
+        out = empty_nhwc(b, n, ho, wo, out_dtype, dev)
+    d = L.ConvDesc()
+    keep = []
+    for i, (t, taps) in enumerate(segs):
+        t = as_nhwc(t)
+        keep.append(t)
+        d.a[i] = t.data_ptr()
+        d.a_c[i] = t.shape[1]
+        d.a_ld[i] = _pix_ld(t)
+        d.a_taps[i] = taps
+    d.nseg = len(segs)
+    d.a_batched = 1 if a_batched else 0
+    d.batch, d.h, d.w = b, h, w
+    d.stride, d.pad = stride, pad
+    d.wt = wt.data_ptr()
+    d.w_bstride = w_bstride
+    d.w_ld = w_ld
+    d.n = n
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.rowbias = rowbias.data_ptr() if rowbias is not None else None
+    d.rowbias_ld = rowbias.stride(0) if rowbias is not None else 0
+    if residual is not None:
+        residual = as_nhwc(residual)
+        if residual.dtype != out.dtype:
+            residual = residual.to(out.dtype)
+        d.residual = residual.data_ptr()
+        d.res_ld = _pix_ld(residual)
+    d.alpha, d.beta, d.act = float(alpha), float(beta), act
+    d.out = out.data_ptr()
+    d.out_ld = _pix_ld(out)
+    d.out_coff = out_coff
+    d.out_dtype = L.dtype_code(out.dtype)
+    d.stats = None
+    d.stats_groups = 0
+    d.flags = flags
+    use_tc = tc_eligible(segs, n, stride, x0.dtype) and wt.dtype == torch.bfloat16
+    if force == 'tc':
+        use_tc = True
+    elif force == 'simt':
+        use_tc = False
+    st = L.stream_ptr(dev)
+    if use_tc:
+        L.check(L.lib().mudiff_conv_tc(C.byref(d), st), 'conv_tc')
+    else:
+        if wt.dtype != x0.dtype:
+            raise RuntimeError("mu-diff_b200: conv_simt needs weights in the activation dtype")
+        L.check(L.lib().mudiff_conv_simt(C.byref(d), L.dtype_code(x0.dtype), st), 'conv_simt')
+    return out
+
+
+# ---------------------------------------------------------------------------------
+# small dense / embeddings
+# ---------------------------------------------------------------------------------
+def linear(x, weight, bias=None, act_in=L.ACT_NONE, act_out=L.ACT_NONE, out=None):
+    """fp32 [B,K] x [J,K]^T (+bias) -> [B,J]."""
+    x = x.float().contiguous() if (x.dtype != torch.float32 or x.stride(-1) != 1) else x
+    b, k = x.shape
+    j = weight.shape[0]
+    if out is None:
+        out = torch.empty((b, j), dtype=torch.float32, device=x.device)
+    rc = L.lib().mudiff_linear(x.data_ptr(), x.stride(0), weight.data_ptr(),
+                               bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0),
+                               b, k, j, act_in, act_out, L.stream_ptr(x.device))
+    L.check(rc, 'linear')
+    return out
+
+
+def timestep_embedding(t, dim, max_positions=10000.0):
+    t = t.to(torch.int64).contiguous()
+    out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    L.check(L.lib().mudiff_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], dim, float(max_positions),
+                                              L.stream_ptr(t.device)), 'timestep_embedding')
+    return out
+
+
+def pixelnorm(z):
+    z = z.float().contiguous()
+    out = torch.empty_like(z)
+    L.check(L.lib().mudiff_pixelnorm(z.data_ptr(), out.data_ptr(), z.shape[0], z.shape[1], L.stream_ptr(z.device)), 'pixelnorm')
+    return out
+
+
+# ---------------------------------------------------------------------------------
+# elementwise glue
+# ---------------------------------------------------------------------------------
+def gate_mul(a, b):
+    a, b = as_nhwc(a), as_nhwc(b)
+    bb, c, h, w = a.shape
+    out = empty_nhwc(bb, c, h, w, a.dtype, a.device)
+    L.check(L.lib().mudiff_gate_mul(a.data_ptr(), _pix_ld(a), b.data_ptr(), _pix_ld(b), out.data_ptr(), _pix_ld(out),
+                                    L.dtype_code(a.dtype), bb * h * w, c, L.stream_ptr(a.device)), 'gate_mul')
+    return out
+
+
+def gate_blend(g, a, b, out=None):
+    g, a, b = as_nhwc(g), as_nhwc(a), as_nhwc(b)
+    bb, c, h, w = a.shape
+    if out is None:
+        out = empty_nhwc(bb, c, h, w, a.dtype, a.device)
+    L.check(L.lib().mudiff_gate_blend(g.data_ptr(), _pix_ld(g), a.data_ptr(), _pix_ld(a), b.data_ptr(), _pix_ld(b),
+                                      out.data_ptr(), _pix_ld(out), L.dtype_code(a.dtype), bb * h * w, c,
+                                      L.stream_ptr(a.device)), 'gate_blend')
+    return out
+
+
+def add_scale(a, b, scale):
+    a, b = as_nhwc(a), as_nhwc(b)
+    if _pix_ld(a) != a.shape[1] or _pix_ld(b) != b.shape[1]:
+        raise RuntimeError("mu-diff_b200: add_scale needs dense tensors")
+    out = empty_nhwc(*a.shape[:1], a.shape[1], a.shape[2], a.shape[3], a.dtype, a.device)
+    L.check(L.lib().mudiff_add_scale(a.data_ptr(), b.data_ptr(), out.data_ptr(), L.dtype_code(a.dtype), a.numel(),
+                                     float(scale), L.stream_ptr(a.device)), 'add_scale')
+    return out
+
+
+def copy_channels(src, dst, coff=0):
+    """dst[:, coff:coff+C] = src (dtype conversion allowed)."""
+    src = as_nhwc(src)
+    b, c, h, w = src.shape
+    dview = dst[:, coff:coff + c]
+    L.check(L.lib().mudiff_copy_channels(src.data_ptr(), _pix_ld(src), L.dtype_code(src.dtype), dview.data_ptr(),
+                                         _pix_ld(dst), L.dtype_code(dst.dtype), b * h * w, c,
+                                         L.stream_ptr(src.device)), 'copy_channels')
+    return dst
+
+
+def concat(tensors, dtype=None):
+    tensors = [as_nhwc(t) for t in tensors]
+    b, _, h, w = tensors[0].shape
+    c = sum(t.shape[1] for t in tensors)
+    out = empty_nhwc(b, c, h, w, dtype or tensors[0].dtype, tensors[0].device)
+    off = 0
+    for t in tensors:
+        copy_channels(t, out, off)
+        off += t.shape[1]
+    return out
+
+
+def gap(x):
+    x = as_nhwc(x)
+    b, c, h, w = x.shape
+    out = torch.empty((b, c), dtype=torch.float32, device=x.device)
+    L.check(L.lib().mudiff_gap(x.data_ptr(), _pix_ld(x), L.dtype_code(x.dtype), out.data_ptr(), b, h * w, c,
+                               L.stream_ptr(x.device)), 'gap')
+    return out
+
+
+def softmax_rows_(x2d, scale=1.0):
+    rows, cols = x2d.shape
+    L.check(L.lib().mudiff_softmax_rows(x2d.data_ptr(), x2d.data_ptr(), L.dtype_code(x2d.dtype), rows, cols,
+                                        float(scale), L.stream_ptr(x2d.device)), 'softmax_rows')
+    return x2d
+
+
+def posterior_update(x01, x02, xt, noise, t, coef1, coef2, logvar):
+    """engine/test.py:150-177 as one kernel (fp32)."""
+    L.require_cuda(x01, x02, xt, noise, t)
+    b = xt.shape[0]
+    per = xt[0].numel()
+    xt = xt.float().contiguous()
+    noise = noise.float().contiguous()
+
+    def prep(x):
+        x = x.float()
+        if x[0].numel() != per:
+            raise RuntimeError("mu-diff_b200: posterior_update shape mismatch")
+        if not x[0].is_contiguous():
+            x = x.contiguous()
+        return x, (x.stride(0) if b > 1 else per)
+
+    x01, s1 = prep(x01)
+    x02, s2 = prep(x02)
+    t = t.to(torch.int64).contiguous()
+    out = torch.empty_like(xt)
+    rc = L.lib().mudiff_posterior_update(x01.data_ptr(), s1, x02.data_ptr(), s2, xt.data_ptr(), noise.data_ptr(),
+                                         t.data_ptr(), coef1.data_ptr(), coef2.data_ptr(), logvar.data_ptr(),
+                                         coef1.numel(), out.data_ptr(), b, per, L.stream_ptr(xt.device))
+    L.check(rc, 'posterior_update')
+    return out

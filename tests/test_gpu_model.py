@@ -1,0 +1,158 @@
+"""GPU parity of the generators and the whole sampling loop against the CPU oracle and the
+reference-generated goldens.  Gates (BASELINE.json north_star):
+    fp32 path : max-abs <= 1e-4
+    bf16 path : relative L2 error <= 2e-2 and |PSNR delta| <= 0.05 dB (PSNR, data_range=1, on [0,1] images,
+                measured against a target image as tools/metric_calc.py:40 does)
+"""
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mudiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module')
+def M():
+    import mudiff_b200
+    assert torch.cuda.is_available()
+    return mudiff_b200
+
+
+def _build(M, cfg, prec, healthy=False):
+    ns = Namespace(**vars(cfg), b200_precision=prec)
+    mod = M.ncsnpp_generator_adagn_feat_healthy if healthy else M.ncsnpp_generator_adagn_feat
+    v1, v2 = ('g1_healthy', 'g2_healthy') if healthy else ('g1', 'g2')
+    sd1, sd2 = O.make_state_dict(cfg, v1, seed=0), O.make_state_dict(cfg, v2, seed=1)
+    g1, g2 = mod.NCSNpp(ns).to(DEV).eval(), mod.NCSNpp_adaptive(ns).to(DEV).eval()
+    g1.load_state_dict(sd1, strict=True)
+    g2.load_state_dict(sd2, strict=True)
+    return ns, g1, g2, sd1, sd2
+
+
+def _to(ts):
+    return [t.to(DEV) for t in ts]
+
+
+@pytest.mark.parametrize('which,tag', [('main', 'nf64_s32'), ('main', 'nf16_s64'), ('healthy', 'nf64_s32')])
+def test_generators_fp32_vs_reference_golden(M, golden_dir, which, tag):
+    g = np.load(os.path.join(golden_dir, f'gen_{which}.npz'))
+    nf, size, batch = (64, 32, 2) if tag == 'nf64_s32' else (16, 64, 1)
+    healthy = which == 'healthy'
+    cfg = O.default_config(num_channels_dae=nf, image_size=size)
+    ns, g1, g2, _, _ = _build(M, cfg, 'fp32', healthy)
+    conds, x_init, latents, _ = O.synthetic_inputs(batch, size, cfg, ncond=2 if healthy else 3, seed=42)
+    t = torch.tensor([3, 1][:batch], dtype=torch.int64, device=DEV)
+    with torch.no_grad():
+        y1 = g1(x_init.to(DEV), *_to(conds), t, latents[0].to(DEV))
+        y2 = g2(x_init.to(DEV), *_to(conds), t, latents[0].to(DEV), torch.from_numpy(g[f'{tag}_g1']).to(DEV))
+    assert y1.dtype == torch.float32 and tuple(y1.shape) == (batch, 1, size, size)
+    np.testing.assert_allclose(y1.cpu().numpy(), g[f'{tag}_g1'], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(y2.cpu().numpy(), g[f'{tag}_g2'], rtol=0, atol=1e-4)
+
+
+def test_sampling_loop_fp32_vs_reference_golden(M, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'gen_main.npz'))
+    cfg = O.default_config(num_channels_dae=64, image_size=32)
+    ns, g1, g2, _, _ = _build(M, cfg, 'fp32')
+    conds, x_init, latents, noises = O.synthetic_inputs(2, 32, cfg, seed=42)
+    co = M.Posterior_Coefficients(ns, DEV)
+    c = _to(conds)
+    x = M.sample_from_model(co, g1, c[0], g2, c[1], c[2], cfg.num_timesteps, x_init.to(DEV), None, ns,
+                            latents=_to(latents), noises=_to(noises))
+    np.testing.assert_allclose(x.cpu().numpy(), g['nf64_s32_sample'], rtol=0, atol=1e-4)
+
+
+def _bf16_gate(out, ref):
+    rel = ((out - ref).norm() / ref.norm()).item()
+    # PSNR of each against a common "ground truth" image (here: an independent target),
+    # both mapped to [0,1] like train.py to_range_0_1 / test_volume.py:285
+    torch.manual_seed(123)
+    target = torch.rand_like(ref)
+    to01 = lambda v: ((v + 1) / 2).clamp(0, 1)
+    d_psnr = abs(O.psnr(to01(out), target) - O.psnr(to01(ref), target))
+    return rel, d_psnr
+
+
+def test_generators_bf16_vs_oracle(M):
+    cfg = O.default_config(num_channels_dae=64, image_size=64)
+    ns, g1, g2, sd1, sd2 = _build(M, cfg, 'bf16')
+    conds, x_init, latents, _ = O.synthetic_inputs(2, 64, cfg, seed=42)
+    t = torch.tensor([3, 1], dtype=torch.int64)
+    r1 = O.generator_forward(sd1, cfg, 'g1', x_init, conds, t, latents[0])
+    r2 = O.generator_forward(sd2, cfg, 'g2', x_init, conds, t, latents[0], pseudo_target=r1)
+    with torch.no_grad():
+        y1 = g1(x_init.to(DEV), *_to(conds), t.to(DEV), latents[0].to(DEV))
+        y2 = g2(x_init.to(DEV), *_to(conds), t.to(DEV), latents[0].to(DEV), r1.to(DEV))
+    for y, r in ((y1, r1), (y2, r2)):
+        rel, dp = _bf16_gate(y.cpu(), r)
+        assert rel <= 2e-2, rel
+        assert dp <= 0.05, dp
+
+
+def test_sampling_loop_bf16_vs_oracle_and_graph(M):
+    cfg = O.default_config(num_channels_dae=64, image_size=64)
+    ns, g1, g2, sd1, sd2 = _build(M, cfg, 'bf16')
+    conds, x_init, latents, noises = O.synthetic_inputs(2, 64, cfg, seed=42)
+    ref = O.sample_from_model(O.PosteriorCoefficients(cfg), sd1, sd2, cfg, conds, x_init, latents, noises)
+    co = M.Posterior_Coefficients(ns, DEV)
+    c = _to(conds)
+    x = M.sample_from_model(co, g1, c[0], g2, c[1], c[2], cfg.num_timesteps, x_init.to(DEV), None, ns,
+                            latents=_to(latents), noises=_to(noises))
+    rel, dp = _bf16_gate(x.cpu(), ref)
+    assert rel <= 2e-2, rel
+    assert dp <= 0.05, dp
+    # whole-loop CUDA graph == eager, bit for bit (same kernels, same order)
+    gs = M.GraphSampler(co, g1, g2, cfg.num_timesteps, 2, 64, cfg.nz, n_cond=3, device=DEV)
+    xg = gs.run(c, x_init.to(DEV), _to(latents), _to(noises))
+    torch.cuda.synchronize()
+    assert gs.launches_per_replay > 0
+    assert torch.equal(xg, x)
+
+
+def test_batch_invariance_bf16(M):
+    """Size-independent property: sample b of a batch equals the same sample run alone."""
+    cfg = O.default_config(num_channels_dae=64, image_size=64)
+    ns, g1, _, _, _ = _build(M, cfg, 'bf16')
+    conds, x_init, latents, _ = O.synthetic_inputs(3, 64, cfg, seed=7)
+    t = torch.tensor([2, 2, 2], dtype=torch.int64, device=DEV)
+    with torch.no_grad():
+        yb = g1(x_init.to(DEV), *_to(conds), t, latents[0].to(DEV))
+        y1 = g1(x_init[1:2].to(DEV), *[c[1:2].to(DEV) for c in conds], t[1:2], latents[0][1:2].to(DEV))
+    assert (yb[1:2] - y1).abs().max().item() <= 1e-5
+
+
+def test_attention_block_vs_oracle(M):
+    """AttnBlockpp alone (4096-token case is covered by the full-size test)."""
+    torch.manual_seed(11)
+    C, H = 128, 16
+    blk = M.layerspp.AttnBlockpp(C, skip_rescale=True, init_scale=0.).to(DEV)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn_like(p) * (0.1 if p.ndim == 2 else 0.2) + (1.0 if p.ndim == 1 and p is blk.GroupNorm_0.weight else 0.0))
+    sd = {f'a.{k}': v.detach().cpu() for k, v in blk.state_dict().items()}
+    x = torch.randn(2, C, H, H)
+    ref = O._G(sd, O.default_config(), 'g1').attn('a', x)
+    for dtype, tol in ((torch.float32, 1e-4), (torch.bfloat16, 5e-2)):
+        y = blk(x.to(DEV).to(dtype))
+        assert (y.float().cpu() - ref).abs().max().item() <= tol, dtype
+
+
+def test_resblock_module_api_nchw_input(M):
+    """Drop-in module call with a plain contiguous NCHW fp32 tensor (reference calling convention)."""
+    torch.manual_seed(12)
+    act = torch.nn.SiLU()
+    blk = M.layerspp.ResnetBlockBigGANpp_Adagn(act, 64, 128, temb_dim=256, zemb_dim=256, down=True, dropout=0.,
+                                               fir=True, fir_kernel=[1, 3, 3, 1], skip_rescale=True, init_scale=1.).to(DEV).eval()
+    x, temb, zemb = torch.randn(2, 64, 16, 16), torch.randn(2, 256), torch.randn(2, 256)
+    sd = {f'all_modules.0.{k}': v.detach().cpu() for k, v in blk.state_dict().items()}
+    g = O._G(sd, O.default_config(), 'g1')
+    ref = g.res('all_modules.0', dict(cin=64, cout=128, up=False, down=True), x, temb, zemb)
+    y = blk(x.to(DEV), temb.to(DEV), zemb.to(DEV))
+    assert tuple(y.shape) == (2, 128, 8, 8)
+    assert (y.cpu() - ref).abs().max().item() <= 1e-4

@@ -1,0 +1,256 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes) and checked
+against the CPU oracle / reference-generated golden vectors.  Tolerances are stated per test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import mudiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def M():
+    import mudiff_b200
+    assert torch.cuda.is_available()
+    return mudiff_b200
+
+
+def _npz(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ------------------------------------------------------------------ FIR ----------
+@pytest.mark.parametrize('name', ['down2', 'up2', 'pre', 'negpad', 'up3down2', 'odd'])
+@pytest.mark.parametrize('layout', ['nchw', 'nhwc'])
+def test_upfirdn2d_golden(M, golden_dir, name, layout):
+    g = _npz(golden_dir, 'fir.npz')
+    up, down, px0, px1, py0, py1 = (int(v) for v in g[f'{name}_p'])
+    x = torch.from_numpy(g[f'{name}_x']).cuda()
+    if layout == 'nhwc':
+        x = x.contiguous(memory_format=torch.channels_last)
+    k = torch.from_numpy(g[f'{name}_k']).cuda()
+    if px0 == py0 and px1 == py1:
+        y = M.upfirdn2d(x, k, up=up, down=down, pad=(px0, px1))
+    else:
+        y = M.upfirdn2d_ada(x, k, up=up, down=down, pad=(px0, px1, py0, py1))
+    assert tuple(y.shape) == g[f'{name}_y'].shape
+    # fp32 FIR, <= 25 taps, different summation order: 2e-6 absolute
+    np.testing.assert_allclose(y.cpu().numpy(), g[f'{name}_y'], rtol=0, atol=2e-6)
+
+
+def test_upfirdn2d_asymmetric_kernel_and_per_axis(M, golden_dir):
+    g = _npz(golden_dir, 'fir.npz')
+    ux, uy, dx, dy, px0, px1, py0, py1 = (int(v) for v in g['asym_p'])
+    y = M.upfirdn2d_ada(torch.from_numpy(g['asym_x']).cuda(), torch.from_numpy(g['asym_k']).cuda(),
+                        up=(ux, uy), down=(dx, dy), pad=(px0, px1, py0, py1))
+    np.testing.assert_allclose(y.cpu().numpy(), g['asym_y'], rtol=0, atol=5e-6)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize('mode', ['up', 'down', 'pre'])
+def test_upfirdn2d_generator_shapes(M, dtype, mode):
+    """The three FIR modes the generators use, channels-last vectorised path."""
+    torch.manual_seed(3)
+    x = torch.randn(2, 64, 32, 32)
+    k = torch.tensor(O.setup_kernel([1, 3, 3, 1]) * (4 if mode == 'up' else 1))
+    kw = dict(up=2, pad=(2, 1)) if mode == 'up' else (dict(down=2, pad=(1, 1)) if mode == 'down' else dict(pad=(2, 2)))
+    ref = O.upfirdn2d(x.to(dtype).float(), k, **kw)
+    xg = x.to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    y = M.upfirdn2d(xg, k.cuda().to(dtype), **kw)
+    assert y.shape == ref.shape
+    tol = 2e-6 if dtype == torch.float32 else (2e-2 if dtype == torch.bfloat16 else 2e-3)
+    np.testing.assert_allclose(y.float().cpu().numpy(), ref.numpy(), rtol=0, atol=tol)
+
+
+def test_upfirdn2d_empty_and_errors(M):
+    y = M.upfirdn2d(torch.zeros(0, 3, 8, 8, device='cuda'), torch.ones(2, 2, device='cuda'), down=2)
+    assert tuple(y.shape) == (0, 3, 4, 4)
+    with pytest.raises(RuntimeError):
+        M.upfirdn2d(torch.zeros(1, 1, 2, 2, device='cuda'), torch.ones(5, 5, device='cuda'))
+
+
+def test_upfirdn2d_backward_matches_autograd_of_oracle(M):
+    torch.manual_seed(4)
+    x = torch.randn(1, 3, 10, 12, requires_grad=True)
+    k = torch.tensor(O.setup_kernel([1, 3, 3, 1]))
+    O.upfirdn2d(x, k, down=2, pad=(1, 1)).square().sum().backward()
+    xg = x.detach().cuda().requires_grad_(True)
+    M.upfirdn2d(xg, k.cuda(), down=2, pad=(1, 1)).square().sum().backward()
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), x.grad.numpy(), rtol=0, atol=1e-5)
+
+
+def test_fused_leaky_relu_golden(M, golden_dir):
+    g = _npz(golden_dir, 'fir.npz')
+    y = M.fused_leaky_relu(torch.from_numpy(g['lrelu_x']).cuda(), torch.from_numpy(g['lrelu_b']).cuda())
+    np.testing.assert_allclose(y.cpu().numpy(), g['lrelu_y'], rtol=0, atol=1e-6)
+    m = M.FusedLeakyReLU(6).cuda()
+    with torch.no_grad():
+        m.bias.copy_(torch.from_numpy(g['lrelu_b']))
+    np.testing.assert_allclose(m(torch.from_numpy(g['lrelu_x']).cuda()).detach().cpu().numpy(), g['lrelu_y'], atol=1e-6)
+
+
+def test_fused_leaky_relu_slope_and_grad(M):
+    torch.manual_seed(5)
+    x = torch.randn(2, 5, 3, 7, requires_grad=True)
+    b = torch.randn(5, requires_grad=True)
+    ref = O.fused_leaky_relu_ref(x, b, 0.1, 1.5)
+    ref.sum().backward()
+    xg, bg = x.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
+    y = M.fused_leaky_relu(xg, bg, 0.1, 1.5)
+    y.sum().backward()
+    np.testing.assert_allclose(y.detach().cpu().numpy(), ref.detach().numpy(), atol=1e-6)
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), x.grad.numpy(), atol=1e-6)
+    np.testing.assert_allclose(bg.grad.cpu().numpy(), b.grad.numpy(), atol=1e-4)
+
+
+# ------------------------------------------------------------------ posterior ----
+def test_posterior_update_golden(M, golden_dir):
+    from argparse import Namespace
+    g = _npz(golden_dir, 'posterior.npz')
+    co = M.Posterior_Coefficients(Namespace(**vars(O.default_config())), 'cuda')
+    T = lambda k: torch.from_numpy(g[k]).cuda()
+    y = M.sample_posterior_combine(co, T('x01'), T('x02'), T('xt'), T('t'), noise=T('noise'))
+    # same fp32 operation order as engine/test.py:152-173; only expf may differ by an ulp
+    np.testing.assert_allclose(y.cpu().numpy(), g['y'], rtol=0, atol=1e-6)
+
+
+# ------------------------------------------------------------------ GroupNorm ----
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('c0,c1', [(64, 0), (256, 128), (128, 64), (64, 256)])
+def test_groupnorm_adagn_silu(M, dtype, c0, c1):
+    from mudiff_b200 import ops
+    torch.manual_seed(6)
+    b, h, w = 2, 16, 24
+    c = c0 + c1
+    groups = min(c // 4, 32)
+    x0 = (torch.randn(b, c0, h, w) * 2 + 0.5).to(dtype)
+    x1 = (torch.randn(b, c1, h, w) - 0.3).to(dtype) if c1 else None
+    gb = torch.randn(b, 2 * c)
+    xc = torch.cat([x0, x1], 1).float() if c1 else x0.float()
+    ref = F.silu(gb[:, :c, None, None] * F.group_norm(xc, groups, eps=1e-6) + gb[:, c:, None, None])
+    srcs = [ops.as_nhwc(x0.cuda())] + ([ops.as_nhwc(x1.cuda())] if c1 else [])
+    gbg = gb.cuda()
+    y = ops.group_norm(srcs, groups, gamma=gbg, beta=gbg[:, c:], gb_bstride=2 * c, act=1)
+    tol = 2e-5 if dtype == torch.float32 else 6e-2
+    np.testing.assert_allclose(y.float().cpu().numpy(), ref.numpy(), rtol=0, atol=tol)
+
+
+# ------------------------------------------------------------------ convolution --
+def _conv_ref(segs, ws, pad1=True):
+    out = 0
+    for (x, taps), w in zip(segs, ws):
+        out = out + F.conv2d(x.float(), w.float(), padding=1 if taps == 9 else 0)
+    return out
+
+
+@pytest.mark.parametrize('cin,cout,h,w', [(1, 64, 20, 24), (64, 1, 16, 16), (24, 40, 9, 11), (64, 64, 16, 16)])
+def test_conv_simt_fp32(M, cin, cout, h, w):
+    from mudiff_b200 import ops
+    torch.manual_seed(7)
+    x = torch.randn(2, cin, h, w)
+    wgt = torch.randn(cout, cin, 3, 3) / (3 * cin ** 0.5)
+    bias = torch.randn(cout)
+    ref = F.conv2d(x, wgt, bias, padding=1)
+    wt = ops.pack_conv_weight(wgt.cuda(), (cin,), torch.float32)
+    y = ops.conv([(ops.as_nhwc(x.cuda()), 9)], wt, cout, bias=bias.cuda(), force='simt')
+    np.testing.assert_allclose(y.cpu().numpy(), ref.numpy(), rtol=0, atol=2e-5)
+
+
+def test_conv_simt_stride2_valid(M):
+    from mudiff_b200 import ops
+    torch.manual_seed(8)
+    x = torch.randn(2, 16, 17, 17)
+    wgt = torch.randn(32, 16, 3, 3) / 12
+    ref = F.conv2d(x, wgt, stride=2, padding=0)
+    y = ops.conv([(ops.as_nhwc(x.cuda()), 9)], ops.pack_conv_weight(wgt.cuda(), (16,), torch.float32), 32,
+                 stride=2, pad=0, force='simt')
+    np.testing.assert_allclose(y.cpu().numpy(), ref.numpy(), rtol=0, atol=2e-5)
+
+
+TC_CASES = {
+    'gemm_1x1':       dict(B=2, H=32, W=32, C=[64], taps=[1], N=64, flags=0),
+    'conv3_n64':      dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=2),
+    'conv3_n256':     dict(B=1, H=32, W=32, C=[128], taps=[9], N=256, flags=2),
+    'conv3_ragged':   dict(B=3, H=24, W=20, C=[64], taps=[9], N=128, flags=2),
+    'conv3_small':    dict(B=2, H=8, W=8, C=[256], taps=[9], N=256, flags=2),
+    'fused_shortcut': dict(B=2, H=32, W=32, C=[64, 128, 64], taps=[9, 1, 1], N=64, flags=2, epi=True),
+    'n384_sigmoid':   dict(B=1, H=32, W=32, C=[192], taps=[9], N=384, flags=2, act=2),
+    'gemm_mode_h1':   dict(B=2, H=1, W=256, C=[128], taps=[1], N=256, flags=0),
+    'many_tiles':     dict(B=8, H=64, W=64, C=[64], taps=[9], N=64, flags=2),
+}
+
+
+@pytest.mark.parametrize('name', list(TC_CASES))
+def test_conv_tc_vs_fp32_reference(M, name):
+    """tcgen05 implicit GEMM on bf16-exact inputs vs fp32 conv: only the accumulation order
+    differs (fp32 accumulate in TMEM) -> 2e-3 * max|ref| absolute with fp32 output."""
+    from mudiff_b200 import ops
+    c = TC_CASES[name]
+    torch.manual_seed(0)
+    B, H, W, N = c['B'], c['H'], c['W'], c['N']
+    segs, segs_cpu, ws, wcpu = [], [], [], []
+    for ci, taps in zip(c['C'], c['taps']):
+        x = torch.randn(B, ci, H, W).to(torch.bfloat16)
+        k = 3 if taps == 9 else 1
+        w = (torch.randn(N, ci, k, k) / (ci * taps) ** 0.5).to(torch.bfloat16)
+        segs.append((ops.as_nhwc(x.cuda()), taps))
+        segs_cpu.append((x, taps))
+        ws.append(ops.pack_conv_weight(w.cuda(), (ci,), torch.bfloat16))
+        wcpu.append(w)
+    ref = _conv_ref(segs_cpu, wcpu)
+    kw = {}
+    if c.get('epi'):
+        bias, rowbias, res = torch.randn(N), torch.randn(B, N), torch.randn(B, N, H, W)
+        ref = 0.7 * (ref + bias[None, :, None, None] + rowbias[:, :, None, None]) + 0.3 * res
+        kw = dict(bias=bias.cuda(), rowbias=rowbias.cuda(), residual=ops.as_nhwc(res.cuda()), alpha=0.7, beta=0.3)
+    if c.get('act') == 2:
+        ref = torch.sigmoid(ref)
+        kw['act'] = 2
+    wt = torch.cat(ws, dim=1).contiguous()
+    out = ops.conv(segs, wt, N, out_dtype=torch.float32, flags=c['flags'], force='tc', **kw)
+    scale = max(ref.abs().max().item(), 1.0)
+    assert (out.cpu() - ref).abs().max().item() <= 2e-3 * scale
+
+
+def test_conv_tc_batched_weights_qk(M):
+    """S[b] = Q[b] K[b]^T * alpha with K taken from a [B, L, 2C] buffer (w_ld, w_bstride)."""
+    from mudiff_b200 import ops
+    torch.manual_seed(1)
+    B, Lt, C = 2, 256, 128
+    qk = torch.randn(B, 2 * C, 1, Lt).to(torch.bfloat16)
+    qkg = ops.as_nhwc(qk.cuda())
+    q, k = qk[:, :C, 0].float(), qk[:, C:, 0].float()            # [B, C, L]
+    ref = torch.einsum('bcl,bcm->blm', q, k) * 0.25              # [B, Lq, Lk]
+    s = ops.conv([(qkg[:, :C], 1)], qkg[:, C:], Lt, pad=0, alpha=0.25, w_bstride=Lt * 2 * C, w_ld=2 * C,
+                 out_dtype=torch.float32, force='tc')
+    got = s.permute(0, 2, 3, 1).reshape(B, Lt, Lt).cpu()
+    assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+def test_softmax_rows(M):
+    from mudiff_b200 import ops
+    torch.manual_seed(2)
+    for dtype, tol in ((torch.float32, 1e-6), (torch.bfloat16, 4e-3)):
+        x = (torch.randn(37, 4096) * 3).to(dtype)
+        ref = F.softmax(x.float(), dim=-1)
+        y = ops.softmax_rows_(x.cuda().clone())
+        np.testing.assert_allclose(y.float().cpu().numpy(), ref.numpy(), rtol=0, atol=tol)
+
+
+def test_small_dense_and_embeddings(M):
+    from mudiff_b200 import ops
+    torch.manual_seed(9)
+    x, w, b = torch.randn(5, 100), torch.randn(300, 100) / 10, torch.randn(300)
+    ref = F.silu(F.linear(F.silu(x), w, b))
+    y = ops.linear(x.cuda(), w.cuda(), b.cuda(), act_in=1, act_out=1)
+    np.testing.assert_allclose(y.cpu().numpy(), ref.numpy(), rtol=0, atol=2e-5)
+    t = torch.tensor([3, 2, 1, 0, 3])
+    np.testing.assert_allclose(ops.timestep_embedding(t.cuda(), 64).cpu().numpy(),
+                               O.timestep_embedding(t, 64).numpy(), rtol=0, atol=2e-6)
+    z = torch.randn(4, 100)
+    np.testing.assert_allclose(ops.pixelnorm(z.cuda()).cpu().numpy(),
+                               (z / torch.sqrt(torch.mean(z ** 2, dim=1, keepdim=True) + 1e-8)).numpy(), atol=1e-6)

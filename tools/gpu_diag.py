@@ -1,0 +1,104 @@
+"""GPU bring-up diagnostics for the tcgen05 conv kernel: every case runs in its own
+subprocess (a device trap in one case must not poison the rest).  Usage on the GPU box:
+    python tools/gpu_diag.py            # all cases
+    python tools/gpu_diag.py CASE       # one case (internal)
+"""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = {
+    # name: (B, H, W, [Cin per seg], [taps per seg], N, flags, extras)
+    'gemm_1x1_n64':      dict(B=2, H=32, W=32, C=[64], taps=[1], N=64, flags=0),
+    'gemm_1x1_k256_n256': dict(B=1, H=16, W=64, C=[256], taps=[1], N=256, flags=0),
+    'conv3_pertap_n64':  dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=2),
+    'conv3_pertap_n256': dict(B=1, H=32, W=32, C=[128], taps=[9], N=256, flags=2),
+    'conv3_halo_n64':    dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=1),
+    'conv3_halo_bo_n64': dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=1 | 4),
+    'conv3_halo_c192':   dict(B=1, H=48, W=40, C=[192], taps=[9], N=64, flags=1),
+    'conv3_ragged':      dict(B=3, H=24, W=20, C=[64], taps=[9], N=128, flags=2),
+    'fused_shortcut':    dict(B=2, H=32, W=32, C=[64, 128, 64], taps=[9, 1, 1], N=64, flags=2, epi=True),
+    'fused_shortcut_halo': dict(B=2, H=32, W=32, C=[64, 128, 64], taps=[9, 1, 1], N=64, flags=1, epi=True),
+    'n384_sigmoid':      dict(B=1, H=32, W=32, C=[192], taps=[9], N=384, flags=2, act=2),
+    'gemm_mode_h1':      dict(B=2, H=1, W=256, C=[128], taps=[1], N=256, flags=0),
+    'many_tiles':        dict(B=8, H=64, W=64, C=[64], taps=[9], N=64, flags=2),
+    'many_tiles_halo':   dict(B=8, H=64, W=64, C=[64], taps=[9], N=64, flags=1),
+}
+
+
+def run_case(name):
+    import torch
+    import torch.nn.functional as F
+    import mudiff_b200 as M
+    from mudiff_b200 import ops
+    c = CASES[name]
+    torch.manual_seed(0)
+    dev = 'cuda'
+    B, H, W, N = c['B'], c['H'], c['W'], c['N']
+    segs, ws, ref = [], [], 0
+    for ci, taps in zip(c['C'], c['taps']):
+        x = torch.randn(B, ci, H, W, device=dev).to(torch.bfloat16)
+        k = 3 if taps == 9 else 1
+        w = (torch.randn(N, ci, k, k, device=dev) / (ci * taps) ** 0.5).to(torch.bfloat16)
+        ref = ref + F.conv2d(x.float(), w.float(), padding=k // 2)
+        segs.append((ops.as_nhwc(x), taps))
+        ws.append(ops.pack_conv_weight(w, (ci,), torch.bfloat16))
+    wt = torch.cat(ws, dim=1).contiguous()
+    kw = {}
+    if c.get('epi'):
+        bias = torch.randn(N, device=dev)
+        rowbias = torch.randn(B, N, device=dev)
+        res = torch.randn(B, N, H, W, device=dev)
+        ref = 0.7 * (ref + bias[None, :, None, None] + rowbias[:, :, None, None]) + 0.3 * res
+        kw = dict(bias=bias, rowbias=rowbias, residual=ops.as_nhwc(res), alpha=0.7, beta=0.3)
+    if c.get('act') == 2:
+        ref = torch.sigmoid(ref)
+        kw['act'] = 2
+    out = ops.conv(segs, wt, N, out_dtype=torch.float32, flags=c['flags'], force='tc', **kw)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    # bf16 output too
+    kw2 = dict(kw)
+    if 'residual' in kw2:
+        kw2['residual'] = kw2['residual'].to(torch.bfloat16)
+    out16 = ops.conv(segs, wt, N, out_dtype=torch.bfloat16, flags=c['flags'], force='tc', **kw2)
+    torch.cuda.synchronize()
+    err16 = (out16.float() - ref).abs().max().item()
+    ok = err < 2e-3 * max(scale, 1.0)
+    print(f"CASE {name}: max|err| f32-out {err:.3e}  bf16-out {err16:.3e}  (|ref|max {scale:.3f})  {'OK' if ok else 'MISMATCH'}")
+    if not ok:
+        d = (out - ref).abs()
+        bad = (d > 1e-2 * max(scale, 1.0))
+        print("   bad fraction", bad.float().mean().item(), " per-channel bad frac (first 8):",
+              bad.float().mean(dim=(0, 2, 3))[:8].tolist())
+        print("   per-row(y) bad frac:", [round(v, 2) for v in bad.float().mean(dim=(0, 1, 3))[:16].tolist()])
+        print("   per-col(x) bad frac:", [round(v, 2) for v in bad.float().mean(dim=(0, 1, 2))[:16].tolist()])
+    return 0 if ok else 1
+
+
+if __name__ == '__main__':
+    if len(sys.argv) > 1:
+        sys.exit(run_case(sys.argv[1]))
+    fails = 0
+    for name in CASES:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=180)
+            lines = [l for l in (r.stdout + r.stderr).splitlines() if l.strip()]
+            tail = [l for l in lines if l.startswith('CASE') or l.startswith('   ')]
+            if r.returncode != 0 and not tail:
+                tail = lines[-6:]
+            print('\n'.join(tail) if tail else f'CASE {name}: no output rc={r.returncode}')
+            if r.returncode != 0:
+                fails += 1
+                print(f'   rc={r.returncode}')
+        except subprocess.TimeoutExpired:
+            fails += 1
+            print(f'CASE {name}: TIMEOUT')
+        print(f'   ({time.time() - t0:.1f}s)', flush=True)
+    print('DIAG FAILS', fails)
