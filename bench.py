@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py - slices/sec of complete 4-step 256x256 MU-Diff sampling (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--batch 64] [--size 256] [--precision bf16|fp32]
+
+A "step" is one pass of the hot path over one batch: the whole 4-step reverse-sampling loop
+(8 generator forwards + 4 posterior updates) for `batch` slices, replayed as ONE CUDA graph.
+Workload = BASELINE.json configs[1]: BraTS T1ce synthesis, batch 64 synthetic 256^2 slices
+[FLAIR,T2,T1 -> T1ce], nf=64, ch_mult 1 2 4, 2 res blocks, random-init weights.
+
+Prints ONE JSON line (rank 0).  Keys: see the driver contract; additionally
+  roofline     : tensor-core roofline of the dominant kernel (tcgen05 implicit-GEMM conv), measured
+                 live with CUDA events around every conv launch of one eager pass on the launching stream
+  cpu_baseline : the oracle port of the reference's CPU path timed on this box's host cores on a
+                 bounded sample (1 slice of the same workload)
+  e2e          : same metric through the public API with pinned-host inputs -> H2D -> device RNG ->
+                 graph replay -> D2H of the synthesized slices, every step.
+`--impl reference` times the reference's own CPU implementation of the path (oracle port; the
+reference is Python and cannot travel to the GPU box) on all host threads.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from argparse import Namespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TFLOP_PER_SLICE = {  # algorithmic FLOPs of one 4-step sample, hooks on the reference modules
+    (64, 128): 0.837, (64, 256): 3.449, (64, 512): 15.446, (128, 256): 13.509,
+}
+METRIC = "slices/sec, 4-step 256^2 MU-Diff sampling"
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tf_sustained=d['bf16_tflops_sustained'], tf_burst=d['bf16_tflops'], hbm=d['hbm_gbs'], src='measured')
+    return dict(tf_sustained=1400.0, tf_burst=1590.0, hbm=6650.0, src='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.sm_max = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap',
+        }
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        import statistics
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons)}
+
+
+def build_cfg(args):
+    return Namespace(num_channels=1, num_channels_dae=args.nf, ch_mult=[1, 2, 4], num_res_blocks=2,
+                     attn_resolutions=[16], dropout=0.0, resamp_with_conv=True, conditional=True, fir=True,
+                     fir_kernel=[1, 3, 3, 1], skip_rescale=True, resblock_type='biggan', progressive='none',
+                     progressive_input='residual', progressive_combine='sum', embedding_type='positional',
+                     fourier_scale=16.0, not_use_tanh=False, image_size=args.size, nz=100, z_emb_dim=256,
+                     t_emb_dim=256, n_mlp=3, centered=True, num_timesteps=4, beta_min=0.1, beta_max=20.0,
+                     use_geometric=False, b200_precision=args.precision)
+
+
+def cpu_oracle_time(args, n_slices=1, repeats=1):
+    """The reference's CPU path (oracle port: plain PyTorch fp32 + upfirdn2d_native restatement)."""
+    import torch
+    from oracle import mudiff_oracle as O
+    cfg = O.default_config(num_channels_dae=args.nf, image_size=args.size)
+    sd1, sd2 = O.make_state_dict(cfg, 'g1', seed=0), O.make_state_dict(cfg, 'g2', seed=1)
+    co = O.PosteriorCoefficients(cfg)
+    conds, x_init, latents, noises = O.synthetic_inputs(n_slices, args.size, cfg, seed=42)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.sample_from_model(co, sd1, sd2, cfg, conds, x_init, latents, noises)
+        times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    n_slices = 1
+    for _ in range(args.warmup):
+        cpu_oracle_time(args, n_slices)
+    times, threads = cpu_oracle_time(args, n_slices, repeats=args.steps)
+    total = sum(times)
+    v = n_slices * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "slices/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": v, "unit": "slices/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_slices} slice/step of the workload (4-step loop, {args.size}^2, nf={args.nf}), CPU fp32"},
+        "e2e": {"value": v, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"BraTS T1ce synthesis sampling, batch {args.batch} synthetic {args.size}^2 slices "
+                        f"[FLAIR,T2,T1->T1ce], NCSN++ G1+G2 nf={args.nf} ch_mult 1 2 4, 4 steps",
+            "global_batch": args.batch * args.gpus, "per_gpu_batch": args.batch, "size": args.size,
+            "precision": args.precision, "parallelism": f"dp{args.gpus} (independent slices, no data-path collective)",
+            "l2": "activations per step >> 126 MB L2 (inputs larger than L2)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--size', type=int, default=256)
+    ap.add_argument('--nf', type=int, default=64)
+    ap.add_argument('--precision', default='bf16')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != 'reference':
+        args.warmup = 3
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import mudiff_b200 as M
+    from mudiff_b200 import ops
+    from mudiff_b200.utils import randomize_
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cfg = build_cfg(args)
+    B, S = args.batch, args.size
+    torch.manual_seed(0)
+    g1 = randomize_(M.NCSNpp(cfg), 0).to(dev).eval()
+    g2 = randomize_(M.NCSNpp_adaptive(cfg), 1).to(dev).eval()
+    co = M.Posterior_Coefficients(cfg, dev)
+
+    # synthetic inputs: cond = clamp(N(0,1), +-3)/3 in pinned host memory
+    gen = torch.Generator().manual_seed(42 + rank)
+    conds_h = [(torch.randn(B, 1, S, S, generator=gen).clamp(-3, 3) / 3).pin_memory() for _ in range(3)]
+    out_h = torch.empty(B, 1, S, S).pin_memory()
+
+    gs = M.GraphSampler(co, g1, g2, cfg.num_timesteps, B, S, cfg.nz, n_cond=3, device=dev, warmup=1)
+    dgen = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def draw_noise():
+        gs.x_init.normal_(generator=dgen)
+        for t in gs.latents:
+            t.normal_(generator=dgen)
+        for t in gs.noises:
+            t.normal_(generator=dgen)
+
+    for d, s in zip(gs.conds, conds_h):
+        d.copy_(s)
+    draw_noise()
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ------------------------------------------------ device-resident timing ------
+    for _ in range(args.warmup):
+        gs.replay()
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        gs.replay()
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    sampler.stop_flag = True
+    sampler.join()
+    t_ms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = t_ms.item()
+    value = B * world * args.steps / (ms_max / 1e3)
+
+    # ------------------------------------------------ end-to-end timing -----------
+    def e2e_step():
+        for d, s in zip(gs.conds, conds_h):
+            d.copy_(s, non_blocking=True)         # H2D from pinned memory
+        draw_noise()                              # x_init / z / noise drawn on the device (as engine/test.py:188,331)
+        y = gs.replay()
+        out_h.copy_(y, non_blocking=True)         # D2H of the synthesized slices
+    e2e_value = None
+    if not args.no_e2e:
+        for _ in range(2):
+            e2e_step()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        sync_all()
+        wall = time.perf_counter() - t0
+        e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+        t_e = torch.tensor([e2e_ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e_value = B * world * args.steps / (t_e.item() / 1e3)
+    h2d = 3 * B * S * S * 4
+    d2h = B * S * S * 4
+
+    # ------------------------------------------------ roofline of the dominant kernel
+    roof = None
+    pk = peaks()
+    if not args.no_roofline and rank == 0:
+        recs = []
+
+        class _Rec:
+            def __init__(self, kind, flops, meta):
+                self.kind, self.flops, self.meta = kind, flops, meta
+                self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+            def __enter__(self):
+                self.a.record()
+
+            def __exit__(self, *exc):
+                self.b.record()
+                recs.append(self)
+
+        ops.set_profiler(lambda kind, flops, meta: _Rec(kind, flops, meta))
+        with torch.no_grad():
+            gs._loop()                    # one eager pass, every conv launch bracketed by events
+        torch.cuda.synchronize(dev)
+        ops.set_profiler(None)
+        tc = [r for r in recs if r.kind == 'conv_tc']
+        tc_ms = sum(r.a.elapsed_time(r.b) for r in tc)
+        tc_flops = sum(r.flops for r in tc)
+        simt_ms = sum(r.a.elapsed_time(r.b) for r in recs if r.kind == 'conv_simt')
+        ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "achieved": ach,
+                "peak": pk['tf_sustained'], "unit": "TFLOP/s", "frac": ach / pk['tf_sustained'], "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
+                "launches": len(tc), "kernel_ms_per_step": tc_ms, "share_of_step": tc_ms / (ms_max / args.steps),
+                "algorithmic_tflop_per_step": tc_flops / 1e12, "conv_simt_ms_per_step": simt_ms}
+    key = (args.nf, S)
+    e2e_frac = None
+    if key in TFLOP_PER_SLICE:
+        e2e_frac = (value / world) * TFLOP_PER_SLICE[key] / pk['tf_sustained']
+
+    # ------------------------------------------------ CPU baseline (rank 0, N == 1) -
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, threads = cpu_oracle_time(args, 1, repeats=1)
+        cpu = {"value": 1.0 / times[0], "unit": "slices/s", "cores": threads, "kind": "port",
+               "sample": f"1 slice of the workload (full 4-step loop, {S}^2, nf={args.nf}, fp32) through the oracle "
+                         f"port of the reference CPU path; {times[0]:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args),
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": gs.launches_per_replay * args.steps,
+            "launches_per_step": gs.launches_per_replay,
+            "roofline": roof, "cpu_baseline": cpu,
+            "tensor_roofline_frac_end_to_end": e2e_frac,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

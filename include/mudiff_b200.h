@@ -88,8 +88,9 @@ int mudiff_posterior_update(const float* x01, int64_t x01_bstride, const float* 
  * Input is the channel-concatenation of up to two NHWC tensors (x0: C0 channels with
  * pixel stride ld0, x1: C1 with ld1; x1 may be NULL) - this is torch.cat([h, hs.pop()], 1)
  * of ncsnpp_generator_adagn_feat.py:383 without materialising it.
- * stats: double[B][G][2] = (sum, sum of squares); mudiff_gn_stats ACCUMULATES into it
- * (caller zeroes it, e.g. with mudiff_zero).  G groups over C0+C1 channels.
+ * stats: double[B][G][2] = (sum, sum of squares), overwritten by mudiff_gn_stats.  The reduction
+ * is deterministic and batch-invariant (fixed 512-pixel blocks, ordered partial sums, no
+ * floating-point atomics).  G groups over C0+C1 channels.
  * apply: y = act(gamma[b,c] * (x-mean)*rstd + beta[b,c]); gamma/beta fp32 with batch
  * stride gb_bstride (0 => shared affine [C]); NULL gamma/beta => 1/0.
  * ------------------------------------------------------------------------------- */

@@ -165,22 +165,6 @@ __global__ void copy_channels_vec_kernel(const T* __restrict__ src, int src_ld, 
   }
 }
 
-// global average pool: grid (chunks, batch); fp32 atomics into out (pre-zeroed by caller? no:
-// two-pass: block partial -> atomicAdd of partial/hw; caller zeroes `out`)
-template <typename T>
-__global__ void gap_kernel(const T* __restrict__ x, int ld, float* __restrict__ out, int64_t hw, int c, float inv) {
-  const int b = blockIdx.y;
-  const T* xb = x + (int64_t)b * hw * ld;
-  // thread -> channel (tid % c), pixel lane (tid / c)
-  const int lanes = blockDim.x / c;
-  const int ch = threadIdx.x % c, lane = threadIdx.x / c;
-  if (lane >= lanes) return;
-  float acc = 0.f;
-  for (int64_t p = (int64_t)blockIdx.x * lanes + lane; p < hw; p += (int64_t)gridDim.x * lanes)
-    acc += Cvt<T>::to_f(xb[p * ld + ch]);
-  atomicAdd(out + (int64_t)b * c + ch, acc * inv);
-}
-
 template <typename TS, typename TD>
 __global__ void tanh_kernel(const TS* __restrict__ x, TD* __restrict__ out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -411,21 +395,6 @@ extern "C" int mudiff_copy_channels(const void* src, int src_ld, int src_dtype, 
   else if (src_dtype == MUDIFF_BF16 && dst_dtype == MUDIFF_BF16) CC(__nv_bfloat16, __nv_bfloat16);
   else return MUDIFF_EUNSUPPORTED;
 #undef CC
-  return mudiff_launch_status();
-}
-
-extern "C" int mudiff_gap(const void* x, int ld, int dtype, float* out, int batch, int64_t hw, int c, void* stream) {
-  if (batch <= 0 || hw <= 0 || c <= 0 || c > 1024) return MUDIFF_EINVAL;
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(out, 0, sizeof(float) * (size_t)batch * c, st);
-  int block = (1024 / c) * c; if (block > 512) block = (512 / c) * c; if (block < c) block = c;
-  int lanes = block / c;
-  int chunks = (int)((hw + lanes * 64 - 1) / (lanes * 64)); if (chunks < 1) chunks = 1; if (chunks > 1024) chunks = 1024;
-  dim3 grid(chunks, batch);
-  float inv = 1.0f / (float)hw;
-  if (dtype == MUDIFF_F32) gap_kernel<float><<<grid, block, 0, st>>>((const float*)x, ld, out, hw, c, inv);
-  else if (dtype == MUDIFF_BF16) gap_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ld, out, hw, c, inv);
-  else return MUDIFF_EUNSUPPORTED;
   return mudiff_launch_status();
 }
 

@@ -9,17 +9,21 @@ namespace {
 
 #define GN_MAX_C 1024
 
+// Deterministic and batch-invariant: a block always owns GN_PPB consecutive pixels of one image,
+// threads reduce in a fixed order, block partials go to `partial[b][chunk][g]` and the LAST block of
+// each image (self-resetting ticket counter) adds them up in chunk order.  No floating-point atomics.
+#define GN_PPB 512
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const T* __restrict__ x1, int c1, int ld1,
-                                int64_t hw, int groups, double* __restrict__ stats, int pix_per_block) {
+                                int64_t hw, int groups, double* __restrict__ stats, double* __restrict__ partial,
+                                unsigned int* __restrict__ tickets) {
   constexpr int V = 16 / sizeof(T);
   const int C = c0 + c1;
   const int cv = C / V;
   const int b = blockIdx.y;
-  __shared__ float s_sum[GN_MAX_C];
-  __shared__ float s_sq[GN_MAX_C];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
-  __syncthreads();
+  const int chunks = gridDim.x;
+  extern __shared__ float s_part[];            // [lanes][C][2]
+  __shared__ bool s_last;
   // blockDim.x is a multiple of cv: each thread keeps one channel vector for the whole loop
   const int my_cv = threadIdx.x % cv;
   const int lane = threadIdx.x / cv;
@@ -31,8 +35,8 @@ __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const
   float sum[V], sq[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { sum[i] = 0.f; sq[i] = 0.f; }
-  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
-  int64_t p1 = p0 + pix_per_block; if (p1 > hw) p1 = hw;
+  const int64_t p0 = (int64_t)blockIdx.x * GN_PPB;
+  int64_t p1 = p0 + GN_PPB; if (p1 > hw) p1 = hw;
   for (int64_t p = p0 + lane; p < p1; p += lanes) {
     float v[V];
     load_vec<T>(base + p * ld + cc, v);
@@ -40,14 +44,38 @@ __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const
     for (int i = 0; i < V; ++i) { sum[i] += v[i]; sq[i] = fmaf(v[i], v[i], sq[i]); }
   }
 #pragma unroll
-  for (int i = 0; i < V; ++i) { atomicAdd(&s_sum[ch + i], sum[i]); atomicAdd(&s_sq[ch + i], sq[i]); }
+  for (int i = 0; i < V; ++i) {
+    s_part[((size_t)lane * C + ch + i) * 2 + 0] = sum[i];
+    s_part[((size_t)lane * C + ch + i) * 2 + 1] = sq[i];
+  }
   __syncthreads();
   const int cpg = C / groups;
+  double* my_partial = partial + ((int64_t)b * chunks + blockIdx.x) * groups * 2;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double a = 0.0, q = 0.0;
-    for (int i = 0; i < cpg; ++i) { a += (double)s_sum[g * cpg + i]; q += (double)s_sq[g * cpg + i]; }
-    atomicAdd(&stats[((int64_t)b * groups + g) * 2 + 0], a);
-    atomicAdd(&stats[((int64_t)b * groups + g) * 2 + 1], q);
+    for (int i = 0; i < cpg; ++i)
+      for (int l = 0; l < lanes; ++l) {
+        a += (double)s_part[((size_t)l * C + g * cpg + i) * 2 + 0];
+        q += (double)s_part[((size_t)l * C + g * cpg + i) * 2 + 1];
+      }
+    my_partial[g * 2 + 0] = a;
+    my_partial[g * 2 + 1] = q;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(&tickets[b], 1u);
+    s_last = (t == (unsigned int)chunks - 1);
+    if (s_last) tickets[b] = 0;                 // self-reset for the next launch on this stream
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double* pb = partial + (int64_t)b * chunks * groups * 2;
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
+    double a = 0.0;
+    for (int k = 0; k < chunks; ++k) a += pb[(int64_t)k * groups * 2 + i];
+    stats[(int64_t)b * groups * 2 + i] = a;
   }
 }
 
@@ -110,6 +138,33 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x0, int c0, int ld0, cons
   }
 }
 
+// scratch for block partials + ticket counters, grown on demand (single stream of use per device)
+struct StatsScratch { double* partial = nullptr; size_t cap = 0; unsigned int* tickets = nullptr; int tcap = 0; };
+static StatsScratch g_scratch[16];
+
+static int ensure_scratch(int dev, size_t need_partial, int need_tickets, cudaStream_t st) {
+  StatsScratch& s = g_scratch[dev];
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (need_partial > s.cap) {
+    if (cs != cudaStreamCaptureStatusNone) return MUDIFF_EUNSUPPORTED;   // must be sized by a warm-up run
+    size_t cap = need_partial * 2; if (cap < (1u << 20)) cap = 1u << 20;
+    double* p = nullptr;
+    if (cudaMalloc(&p, cap * sizeof(double)) != cudaSuccess) return (int)cudaGetLastError();
+    // old buffer is leaked on purpose while kernels of earlier launches may still read it (tiny)
+    s.partial = p; s.cap = cap;
+  }
+  if (need_tickets > s.tcap) {
+    if (cs != cudaStreamCaptureStatusNone) return MUDIFF_EUNSUPPORTED;
+    int cap = need_tickets * 2; if (cap < 4096) cap = 4096;
+    unsigned int* t = nullptr;
+    if (cudaMalloc(&t, cap * sizeof(unsigned int)) != cudaSuccess) return (int)cudaGetLastError();
+    cudaMemset(t, 0, cap * sizeof(unsigned int));
+    s.tickets = t; s.tcap = cap;
+  }
+  return 0;
+}
+
 template <typename T>
 int launch_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int batch, int64_t hw,
                  int groups, double* stats, cudaStream_t st) {
@@ -120,14 +175,16 @@ int launch_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld
   const int cv = C / V;
   int block = (256 / cv) * cv;
   if (block < cv) block = cv;                // cv <= 256 since C <= 1024, V >= 4
-  // enough blocks to fill the machine ~4x, at least 64 pixels per lane-iteration set
-  int64_t want = (int64_t)MUDIFF_NUM_SMS * 8 / (batch > 0 ? batch : 1);
-  if (want < 1) want = 1;
-  int64_t ppb = (hw + want - 1) / want;
-  if (ppb < 256) ppb = 256;
-  int chunks = (int)((hw + ppb - 1) / ppb);
+  const int lanes = block / cv;
+  int chunks = (int)((hw + GN_PPB - 1) / GN_PPB);
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
+  int rc = ensure_scratch(dev, (size_t)batch * chunks * groups * 2, batch, st);
+  if (rc) return rc;
   dim3 grid(chunks, batch);
-  gn_stats_kernel<T><<<grid, block, 0, st>>>((const T*)x0, c0, ld0, (const T*)x1, c1, ld1, hw, groups, stats, (int)ppb);
+  size_t smem = sizeof(float) * 2 * (size_t)lanes * C;
+  gn_stats_kernel<T><<<grid, block, smem, st>>>((const T*)x0, c0, ld0, (const T*)x1, c1, ld1, hw, groups, stats,
+                                               g_scratch[dev].partial, g_scratch[dev].tickets);
   return mudiff_launch_status();
 }
 
@@ -150,7 +207,41 @@ int launch_apply(const void* x0, int c0, int ld0, const void* x1, int c1, int ld
   return mudiff_launch_status();
 }
 
+__global__ void gap_mean_kernel(const double* __restrict__ stats, float* __restrict__ out, int n, double inv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)(stats[2 * i] * inv);
+}
+
 }  // namespace
+
+// Global average pool = per-channel sums of the deterministic statistics kernel (groups == C).
+extern "C" int mudiff_gap(const void* x, int ld, int dtype, float* out, int batch, int64_t hw, int c, void* stream) {
+  if (batch <= 0 || hw <= 0 || c <= 0 || c > GN_MAX_C || !x || !out) return MUDIFF_EINVAL;
+  if (batch > 65535) return MUDIFF_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  static double* gap_stats[16] = {nullptr};
+  static size_t gap_cap[16] = {0};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
+  size_t need = (size_t)batch * c * 2;
+  if (need > gap_cap[dev]) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return MUDIFF_EUNSUPPORTED;
+    size_t cap = need * 2; if (cap < 65536) cap = 65536;
+    double* p = nullptr;
+    if (cudaMalloc(&p, cap * sizeof(double)) != cudaSuccess) return (int)cudaGetLastError();
+    gap_stats[dev] = p; gap_cap[dev] = cap;
+  }
+  int rc;
+  if (dtype == MUDIFF_F32) rc = launch_stats<float>(x, c, ld, nullptr, 0, 0, batch, hw, c, gap_stats[dev], st);
+  else if (dtype == MUDIFF_BF16) rc = launch_stats<__nv_bfloat16>(x, c, ld, nullptr, 0, 0, batch, hw, c, gap_stats[dev], st);
+  else return MUDIFF_EUNSUPPORTED;
+  if (rc) return rc;
+  int n = batch * c;
+  gap_mean_kernel<<<(n + 255) / 256, 256, 0, st>>>(gap_stats[dev], out, n, 1.0 / (double)hw);
+  return mudiff_launch_status();
+}
 
 extern "C" int mudiff_gn_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int dtype,
                                int batch, int64_t hw, int groups, double* stats, void* stream) {

@@ -13,6 +13,14 @@ from . import _lib as L
 
 SQRT2_INV = 1.0 / math.sqrt(2.0)
 
+# Optional per-launch profiler (bench.py): callable(kind, flops, bytes) -> context manager or None.
+_PROFILER = None
+
+
+def set_profiler(fn):
+    global _PROFILER
+    _PROFILER = fn
+
 
 # ---------------------------------------------------------------------------------
 # layout helpers
@@ -119,7 +127,7 @@ def gn_stats(srcs, groups):
     x0 = srcs[0]
     x1 = srcs[1] if len(srcs) > 1 else None
     b, c0, h, w = x0.shape
-    stats = torch.zeros((b, groups, 2), dtype=torch.float64, device=x0.device)
+    stats = torch.empty((b, groups, 2), dtype=torch.float64, device=x0.device)
     rc = L.lib().mudiff_gn_stats(x0.data_ptr(), c0, _pix_ld(x0),
                                  x1.data_ptr() if x1 is not None else None,
                                  x1.shape[1] if x1 is not None else 0, _pix_ld(x1) if x1 is not None else 0,
@@ -232,12 +240,20 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
     elif force == 'simt':
         use_tc = False
     st = L.stream_ptr(dev)
+    prof = None
+    if _PROFILER is not None:
+        ktot = sum(t.shape[1] * taps for t, taps in segs)
+        prof = _PROFILER('conv_tc' if use_tc else 'conv_simt', 2.0 * b * ho * wo * n * ktot,
+                         dict(n=n, ktot=ktot, pixels=b * ho * wo))
+        prof.__enter__()
     if use_tc:
         L.check(L.lib().mudiff_conv_tc(C.byref(d), st), 'conv_tc')
     else:
         if wt.dtype != x0.dtype:
             raise RuntimeError("mu-diff_b200: conv_simt needs weights in the activation dtype")
         L.check(L.lib().mudiff_conv_simt(C.byref(d), L.dtype_code(x0.dtype), st), 'conv_simt')
+    if prof is not None:
+        prof.__exit__(None, None, None)
     return out
 
 
