@@ -161,6 +161,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--breakdown', default='', help="write a per-kernel event-time breakdown to this file ('-' = stderr only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != 'reference':
         args.warmup = 3
@@ -279,11 +280,52 @@ def main():
                 self.b.record()
                 recs.append(self)
 
+        allrecs = []
+
+        class _Call:
+            def __init__(self, name):
+                self.name = name
+                self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+            def __enter__(self):
+                self.a.record()
+
+            def __exit__(self, *exc):
+                self.b.record()
+                allrecs.append(self)
+
         ops.set_profiler(lambda kind, flops, meta: _Rec(kind, flops, meta))
+        if args.breakdown:
+            M._lib.set_call_profiler(_Call)
         with torch.no_grad():
             gs._loop()                    # one eager pass, every conv launch bracketed by events
         torch.cuda.synchronize(dev)
         ops.set_profiler(None)
+        M._lib.set_call_profiler(None)
+        if args.breakdown:
+            agg = {}
+            for r in allrecs:
+                a = agg.setdefault(r.name, [0, 0.0])
+                a[0] += 1
+                a[1] += r.a.elapsed_time(r.b)
+            tot = sum(v[1] for v in agg.values())
+            lines = [f"# per-entry-point CUDA-event time of one eager step (batch {B}, {S}^2, {args.precision}); total {tot:.2f} ms"]
+            for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                lines.append(f"{v[1]:10.3f} ms {100 * v[1] / tot:5.1f}%  n={v[0]:5d}  {k}")
+            shapes = {}
+            for r in recs:
+                key = (r.kind, r.meta['pixels'], r.meta['n'], r.meta['ktot'])
+                a = shapes.setdefault(key, [0, 0.0, 0.0])
+                a[0] += 1
+                a[1] += r.a.elapsed_time(r.b)
+                a[2] += r.flops
+            lines.append("# conv launches by shape: kind pixels N Ktot | n  total_ms  TFLOP/s")
+            for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+                lines.append(f"{k[0]:9s} M={k[1]:8d} N={k[2]:4d} K={k[3]:5d} | n={v[0]:3d} {v[1]:9.3f} ms {v[2] / (v[1] * 1e-3) / 1e12:8.1f}")
+            sys.stderr.write("\n".join(lines) + "\n")
+            if args.breakdown != '-':
+                os.makedirs(os.path.dirname(os.path.abspath(args.breakdown)), exist_ok=True)
+                open(args.breakdown, 'w').write("\n".join(lines) + "\n")
         tc = [r for r in recs if r.kind == 'conv_tc']
         tc_ms = sum(r.a.elapsed_time(r.b) for r in tc)
         tc_flops = sum(r.flops for r in tc)

@@ -66,6 +66,32 @@ PROTOTYPES = {
 _RESTYPES = {'mudiff_build_info': C.c_char_p, 'mudiff_launch_count': C.c_int64}
 
 _lib = None
+_CALL_PROFILER = None       # callable(name) -> context manager; used by bench.py for per-kernel timing
+
+
+def set_call_profiler(fn):
+    global _CALL_PROFILER
+    _CALL_PROFILER = fn
+
+
+class _Proxy:
+    """Thin attribute proxy over the CDLL so that every entry point can be bracketed by CUDA events
+    when a profiler is installed (zero extra work otherwise)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        for name in PROTOTYPES:
+            setattr(self, name, self._wrap(name, getattr(cdll, name)))
+
+    @staticmethod
+    def _wrap(name, fn):
+        def call(*args):
+            prof = _CALL_PROFILER
+            if prof is None:
+                return fn(*args)
+            with prof(name):
+                return fn(*args)
+        return call
 
 
 def lib():
@@ -83,7 +109,7 @@ def lib():
             fn.restype = _RESTYPES.get(name, C.c_int)
         if l.mudiff_conv_desc_size() != C.sizeof(ConvDesc):
             raise RuntimeError('mu-diff_b200: ConvDesc layout mismatch between _lib.py and the shared library')
-        _lib = l
+        _lib = _Proxy(l)
     return _lib
 
 

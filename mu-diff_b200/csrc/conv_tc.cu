@@ -423,9 +423,10 @@ extern "C" int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream) {
   if (!n_tile) return MUDIFF_EUNSUPPORTED;
   p.n_tile = n_tile; p.n_tiles = d->n / n_tile;
   // A staging mode
-  bool want_halo = (d->flags & 1) != 0;
+  // halo staging by default whenever it applies (N <= 64: the A operand dominates L2->smem traffic)
+  bool want_halo = true;
   if (d->flags & 2) want_halo = false;
-  if (!any9 || d->w < 8 || n_tile > 64) want_halo = false;
+  if (!any9 || d->w < 8 || d->h < 2 || n_tile > 64) want_halo = false;
   if (want_halo) { p.tile_w = 8; p.tile_h = 16; }
   else if (d->h == 1) { p.tile_w = 128; p.tile_h = 1; }
   else if (d->w >= 16) { p.tile_w = 16; p.tile_h = 8; }

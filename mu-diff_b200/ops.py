@@ -13,6 +13,9 @@ from . import _lib as L
 
 SQRT2_INV = 1.0 / math.sqrt(2.0)
 
+import os as _os
+_ENV_FLAGS = 2 if _os.environ.get('MUDIFF_HALO', '1') == '0' else 0     # debug knob: forbid halo staging
+
 # Optional per-launch profiler (bench.py): callable(kind, flops, bytes) -> context manager or None.
 _PROFILER = None
 
@@ -233,7 +236,7 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
     d.out_dtype = L.dtype_code(out.dtype)
     d.stats = None
     d.stats_groups = 0
-    d.flags = flags
+    d.flags = flags | _ENV_FLAGS
     use_tc = tc_eligible(segs, n, stride, x0.dtype) and wt.dtype == torch.bfloat16
     if force == 'tc':
         use_tc = True
