@@ -144,12 +144,75 @@ __global__ void fir_nchw_tiled_kernel(const T* __restrict__ in, T* __restrict__ 
   }
 }
 
+// Specialised NHWC kernel for the three modes the generators use (4x4 FIR): UP/DOWN in {1,2}.
+// One block per output row, a thread owns one 16-byte channel vector and walks the row; the
+// taps are compile-time unrolled (polyphase: up=2 touches 2x2 inputs, down=2 touches 4x4).
+template <typename T, int UP, int DOWN>
+__global__ void __launch_bounds__(256) fir4_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                        const float* __restrict__ kern, FirP p) {
+  constexpr int V = 16 / sizeof(T);
+  __shared__ float sk[16];
+  if (threadIdx.x < 16) {
+    int ky = threadIdx.x / 4, kx = threadIdx.x % 4;
+    sk[threadIdx.x] = kern[(3 - ky) * 4 + (3 - kx)];
+  }
+  __syncthreads();
+  float kf[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kf[i] = sk[i];
+  const int cv = p.minor / V;
+  const int row = blockIdx.x;                       // m * out_h + oy
+  const int m = row / p.out_h, oy = row - m * p.out_h;
+  const int c = (threadIdx.x % cv) * V;
+  const int lane = threadIdx.x / cv, lanes = blockDim.x / cv;
+  const T* inm = in + (int64_t)m * p.in_h * p.in_w * p.minor + c;
+  T* orow = out + ((int64_t)row * p.out_w) * p.minor + c;
+  const int by = oy * DOWN - p.py0;
+  for (int ox = lane; ox < p.out_w; ox += lanes) {
+    const int bx = ox * DOWN - p.px0;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int yy = by + ky;
+      if (UP == 2 && (yy & 1)) continue;
+      const int iy = UP == 2 ? yy >> 1 : yy;
+      if (yy < 0 || iy >= p.in_h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int xx = bx + kx;
+        if (UP == 2 && (xx & 1)) continue;
+        const int ix = UP == 2 ? xx >> 1 : xx;
+        if (xx < 0 || ix >= p.in_w) continue;
+        float v[V];
+        load_vec<T>(inm + ((int64_t)iy * p.in_w + ix) * p.minor, v);
+        const float w = kf[ky * 4 + kx];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+      }
+    }
+    store_vec<T>(orow + (int64_t)ox * p.minor, acc);
+  }
+}
+
 template <typename T>
 int launch_fir(const void* in, void* out, const float* kern, const FirP& p, cudaStream_t st) {
   constexpr int V = 16 / sizeof(T);
   const int64_t total = p.major * p.out_h * p.out_w * p.minor;
   if (total == 0) return 0;
   const bool aligned = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  if (p.minor % V == 0 && aligned && p.kh == 4 && p.kw == 4 && p.up_x == p.up_y && p.down_x == p.down_y &&
+      p.up_x <= 2 && p.down_x <= 2 && !(p.up_x == 2 && p.down_x == 2) && p.minor / V <= 256 &&
+      p.major * p.out_h < (1LL << 31)) {
+    const int cv = p.minor / V;
+    const int block = (256 / cv) * cv;
+    const unsigned rows = (unsigned)(p.major * p.out_h);
+    if (p.up_x == 2) fir4_nhwc_kernel<T, 2, 1><<<rows, block, 0, st>>>((const T*)in, (T*)out, kern, p);
+    else if (p.down_x == 2) fir4_nhwc_kernel<T, 1, 2><<<rows, block, 0, st>>>((const T*)in, (T*)out, kern, p);
+    else fir4_nhwc_kernel<T, 1, 1><<<rows, block, 0, st>>>((const T*)in, (T*)out, kern, p);
+    return mudiff_launch_status();
+  }
   if (p.minor % V == 0 && aligned) {
     int grid = grid_for(total / V, 256);
     fir_nhwc_vec_kernel<T><<<grid, 256, 0, st>>>((const T*)in, (T*)out, kern, p);

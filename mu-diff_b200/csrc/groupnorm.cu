@@ -79,61 +79,77 @@ __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const
   }
 }
 
+// apply: each thread owns ONE channel vector (scale/shift live in registers) and walks pixels with a
+// fixed stride -> no integer division in the streaming loop, 4 independent 16-byte loads in flight.
+#define GN_APPLY_PPB 1024
 template <typename TI, typename TO>
 __global__ void gn_apply_kernel(const TI* __restrict__ x0, int c0, int ld0, const TI* __restrict__ x1, int c1, int ld1,
                                 const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int64_t gb_bstride, TO* __restrict__ out, int ld_out,
-                                int64_t hw, int groups, float eps, int act, int pix_per_block) {
-  // vector width is chosen on the WIDER of the two element types so both sides stay 16-byte (or less) aligned
+                                int64_t hw, int groups, float eps, int act) {
+  // vector width is chosen on the WIDER of the two element types so both sides stay <= 16 bytes
   constexpr int V = (sizeof(TI) >= sizeof(TO)) ? 16 / sizeof(TI) : 16 / sizeof(TO);
   const int C = c0 + c1;
   const int cv = C / V;
   const int b = blockIdx.y;
-  __shared__ float s_scale[GN_MAX_C];
-  __shared__ float s_shift[GN_MAX_C];
+  const int my_cv = threadIdx.x % cv;
+  const int lane = threadIdx.x / cv;
+  const int lanes = blockDim.x / cv;
+  const int ch = my_cv * V;
   const int cpg = C / groups;
   const double cnt = (double)hw * (double)cpg;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  float sc[V], sh[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int c = ch + k;
     const int g = c / cpg;
-    double m = stats[((int64_t)b * groups + g) * 2 + 0] / cnt;
+    const double m = stats[((int64_t)b * groups + g) * 2 + 0] / cnt;
     double var = stats[((int64_t)b * groups + g) * 2 + 1] / cnt - m * m;
     if (var < 0.0) var = 0.0;
-    float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    float ga = gamma ? gamma[(int64_t)b * gb_bstride + c] : 1.f;
-    float be = beta ? beta[(int64_t)b * gb_bstride + c] : 0.f;
-    float sc = ga * rstd;
-    s_scale[c] = sc;
-    s_shift[c] = be - (float)m * sc;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = gamma ? gamma[(int64_t)b * gb_bstride + c] : 1.f;
+    const float be = beta ? beta[(int64_t)b * gb_bstride + c] : 0.f;
+    sc[k] = ga * rstd;
+    sh[k] = be - (float)m * sc[k];
   }
-  __syncthreads();
-  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
-  int64_t p1 = p0 + pix_per_block; if (p1 > hw) p1 = hw;
-  const int64_t total = (p1 - p0) * cv;
-  const TI* b0 = x0 + (int64_t)b * hw * ld0;
-  const TI* b1 = x1 ? x1 + (int64_t)b * hw * ld1 : nullptr;
-  TO* ob = out + (int64_t)b * hw * ld_out;
-  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-    const int64_t p = p0 + i / cv;
-    const int ch = (int)(i % cv) * V;
-    const TI* src = ch < c0 ? b0 + p * ld0 + ch : b1 + p * ld1 + (ch - c0);
-    float v[V];
-    if constexpr (V * sizeof(TI) == 16) {
-      load_vec<TI>(src, *reinterpret_cast<float(*)[16 / sizeof(TI)]>(v));
-    } else {
+  const TI* src; int ld;
+  if (ch < c0) { src = x0 + (int64_t)b * hw * ld0 + ch; ld = ld0; }
+  else { src = x1 + (int64_t)b * hw * ld1 + (ch - c0); ld = ld1; }
+  TO* dst = out + (int64_t)b * hw * ld_out + ch;
+  const int64_t p0 = (int64_t)blockIdx.x * GN_APPLY_PPB;
+  int64_t p1 = p0 + GN_APPLY_PPB; if (p1 > hw) p1 = hw;
+  constexpr int U = 4;
+  for (int64_t p = p0 + lane; p < p1; p += (int64_t)lanes * U) {
+    float v[U][V];
 #pragma unroll
-      for (int k = 0; k < V; ++k) v[k] = Cvt<TI>::to_f(src[k]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t pp = p + (int64_t)u * lanes;
+      if (pp < p1) {
+        if constexpr (V * sizeof(TI) == 16) {
+          load_vec<TI>(src + pp * ld, *reinterpret_cast<float(*)[16 / sizeof(TI)]>(v[u]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[u][k] = Cvt<TI>::to_f(src[pp * ld + k]);
+        }
+      }
     }
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float t = fmaf(v[k], s_scale[ch + k], s_shift[ch + k]);
-      v[k] = act == MUDIFF_ACT_SILU ? silu_exact(t) : t;
-    }
-    TO* dst = ob + p * ld_out + ch;
-    if constexpr (V * sizeof(TO) == 16) {
-      store_vec<TO>(dst, *reinterpret_cast<float(*)[16 / sizeof(TO)]>(v));
-    } else {
+    for (int u = 0; u < U; ++u) {
+      const int64_t pp = p + (int64_t)u * lanes;
+      if (pp < p1) {
 #pragma unroll
-      for (int k = 0; k < V; ++k) dst[k] = Cvt<TO>::from_f(v[k]);
+        for (int k = 0; k < V; ++k) {
+          float t = fmaf(v[u][k], sc[k], sh[k]);
+          if (act == MUDIFF_ACT_SILU) t = (sizeof(TO) == 4) ? silu_exact(t) : silu_f(t);
+          v[u][k] = t;
+        }
+        if constexpr (V * sizeof(TO) == 16) {
+          store_vec<TO>(dst + pp * ld_out, *reinterpret_cast<float(*)[16 / sizeof(TO)]>(v[u]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) dst[pp * ld_out + k] = Cvt<TO>::from_f(v[u][k]);
+        }
+      }
     }
   }
 }
@@ -196,14 +212,13 @@ int launch_apply(const void* x0, int c0, int ld0, const void* x1, int c1, int ld
   const int C = c0 + c1;
   if (C % V || c0 % V || ld0 % V || (x1 && ld1 % V) || ld_out % V || C > GN_MAX_C || C % groups) return MUDIFF_EUNSUPPORTED;
   if (((uintptr_t)x0 % 16) || (x1 && ((uintptr_t)x1 % 16)) || ((uintptr_t)out % 16)) return MUDIFF_EUNSUPPORTED;
-  int64_t want = (int64_t)MUDIFF_NUM_SMS * 8 / (batch > 0 ? batch : 1);
-  if (want < 1) want = 1;
-  int64_t ppb = (hw + want - 1) / want;
-  if (ppb < 128) ppb = 128;
-  int chunks = (int)((hw + ppb - 1) / ppb);
+  const int cv = C / V;
+  int block = (256 / cv) * cv;
+  if (block < cv) block = cv;
+  int chunks = (int)((hw + GN_APPLY_PPB - 1) / GN_APPLY_PPB);
   dim3 grid(chunks, batch);
-  gn_apply_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)x0, c0, ld0, (const TI*)x1, c1, ld1, stats, gamma, beta, gbs,
-                                                (TO*)out, ld_out, hw, groups, eps, act, (int)ppb);
+  gn_apply_kernel<TI, TO><<<grid, block, 0, st>>>((const TI*)x0, c0, ld0, (const TI*)x1, c1, ld1, stats, gamma, beta, gbs,
+                                                  (TO*)out, ld_out, hw, groups, eps, act);
   return mudiff_launch_status();
 }
 
