@@ -53,8 +53,14 @@ __device__ __forceinline__ void store_vec(T* p, const float (&v)[16 / sizeof(T)]
   *reinterpret_cast<uint4*>(p) = raw;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// fast variants for bf16 outputs: silu(x) = h + h*tanh(h), h = x/2 -> ONE MUFU op (tanh.approx, rel err ~2^-11)
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_f(float x) { const float h = 0.5f * x; return fmaf(h, tanh_approx(h), h); }
+__device__ __forceinline__ float sigmoid_f(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 // exact-ish variants for the fp32 parity path
 __device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float sigmoid_exact(float x) { return 1.0f / (1.0f + expf(-x)); }

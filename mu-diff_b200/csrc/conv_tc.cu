@@ -485,15 +485,18 @@ extern "C" int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream) {
   const size_t smem_bytes = (size_t)stages * p.stage_bytes + tail + 1024;
   int grid = p.total_tiles < MUDIFF_NUM_SMS ? p.total_tiles : MUDIFF_NUM_SMS;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e;
-  if (d->out_dtype == MUDIFF_F32) {
-    e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  // opt in to the full 227 KB of dynamic shared memory once per kernel instantiation (per device)
+  static bool attr_set[16][2] = {};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
+  const int which = d->out_dtype == MUDIFF_F32 ? 1 : 0;
+  if (!attr_set[dev][which]) {
+    cudaError_t e = which ? cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)
+                          : cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return (int)e;
-    conv_tc_kernel<true><<<grid, kThreads, smem_bytes, st>>>(maps[0], maps[1], maps[2], mapw, p);
-  } else {
-    e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return (int)e;
-    conv_tc_kernel<false><<<grid, kThreads, smem_bytes, st>>>(maps[0], maps[1], maps[2], mapw, p);
+    attr_set[dev][which] = true;
   }
+  if (which) conv_tc_kernel<true><<<grid, kThreads, smem_bytes, st>>>(maps[0], maps[1], maps[2], mapw, p);
+  else conv_tc_kernel<false><<<grid, kThreads, smem_bytes, st>>>(maps[0], maps[1], maps[2], mapw, p);
   return mudiff_launch_status();
 }

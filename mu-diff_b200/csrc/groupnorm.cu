@@ -37,11 +37,22 @@ __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const
   for (int i = 0; i < V; ++i) { sum[i] = 0.f; sq[i] = 0.f; }
   const int64_t p0 = (int64_t)blockIdx.x * GN_PPB;
   int64_t p1 = p0 + GN_PPB; if (p1 > hw) p1 = hw;
-  for (int64_t p = p0 + lane; p < p1; p += lanes) {
-    float v[V];
-    load_vec<T>(base + p * ld + cc, v);
+  constexpr int U = 4;
+  for (int64_t p = p0 + lane; p < p1; p += (int64_t)lanes * U) {
+    float v[U][V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) { sum[i] += v[i]; sq[i] = fmaf(v[i], v[i], sq[i]); }
+    for (int u = 0; u < U; ++u) {
+      const int64_t pp = p + (int64_t)u * lanes;
+      if (pp < p1) load_vec<T>(base + pp * ld + cc, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t pp = p + (int64_t)u * lanes;
+      if (pp < p1) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { sum[i] += v[u][i]; sq[i] = fmaf(v[u][i], v[u][i], sq[i]); }
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < V; ++i) {
