@@ -246,8 +246,62 @@ __global__ void pixelnorm_kernel(const float* __restrict__ z, float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------
-// row softmax: one block per row, row cached in registers (cols <= 256 * 8 * ITER)
+// row softmax.  Fast path: cols == 256 * VEC * R (R <= 4): the row lives in registers (16-byte loads),
+// two block reductions, one pass over HBM each way.  Generic path: row staged in shared memory.
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = (threadIdx.x & 31) < (blockDim.x >> 5) ? red[threadIdx.x & 31] : -INFINITY;
+  for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = (threadIdx.x & 31) < (blockDim.x >> 5) ? red[threadIdx.x & 31] : 0.f;
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  __syncthreads();
+  return r;
+}
+
+template <typename T, int R>
+__global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                               int64_t rows, int cols, float scale) {
+  constexpr int V = 16 / sizeof(T);
+  __shared__ float red[32];
+  const float sl2 = scale * 1.4426950408889634f;      // exp(s*x - m) = exp2(s*log2e*x - m')
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const T* xr = x + r * (int64_t)cols;
+    T* yr = y + r * (int64_t)cols;
+    float v[R][V];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      load_vec<T>(xr + (j * 256 + threadIdx.x) * V, v[j]);
+#pragma unroll
+      for (int k = 0; k < V; ++k) { v[j][k] *= sl2; mx = fmaxf(mx, v[j][k]); }
+    }
+    mx = block_reduce_max(mx, red);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+      for (int k = 0; k < V; ++k) { v[j][k] = exp2f(v[j][k] - mx); s += v[j][k]; }
+    s = block_reduce_sum(s, red);
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[j][k] *= inv;
+      store_vec<T>(yr + (j * 256 + threadIdx.x) * V, v[j]);
+    }
+  }
+}
+
 template <typename T>
 __global__ void softmax_rows_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int cols, float scale) {
   extern __shared__ float row[];            // cols floats
@@ -261,36 +315,38 @@ __global__ void softmax_rows_kernel(const T* __restrict__ x, T* __restrict__ y, 
       row[i] = v;
       mx = fmaxf(mx, v);
     }
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
-      for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-      if (threadIdx.x == 0) red[0] = v;
-    }
-    __syncthreads();
-    mx = red[0];
-    __syncthreads();
+    mx = block_reduce_max(mx, red);
     float s = 0.f;
     for (int i = threadIdx.x; i < cols; i += blockDim.x) {
       float e = expf(row[i] - mx);
       row[i] = e;
       s += e;
     }
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (threadIdx.x == 0) red[0] = v;
-    }
-    __syncthreads();
-    const float inv = 1.0f / red[0];
+    s = block_reduce_sum(s, red);
+    const float inv = 1.0f / s;
     for (int i = threadIdx.x; i < cols; i += blockDim.x) yr[i] = Cvt<T>::from_f(row[i] * inv);
     __syncthreads();
   }
+}
+
+template <typename T>
+int launch_softmax(const void* x, void* y, int64_t rows, int cols, float scale, cudaStream_t st) {
+  constexpr int V = 16 / sizeof(T);
+  const bool al = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+  int grid = (int)(rows < MUDIFF_NUM_SMS * 16 ? rows : MUDIFF_NUM_SMS * 16);
+  if (al && cols % (256 * V) == 0 && cols / (256 * V) <= 4) {
+    switch (cols / (256 * V)) {
+      case 1: softmax_rows_reg_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (T*)y, rows, cols, scale); break;
+      case 2: softmax_rows_reg_kernel<T, 2><<<grid, 256, 0, st>>>((const T*)x, (T*)y, rows, cols, scale); break;
+      case 3: softmax_rows_reg_kernel<T, 3><<<grid, 256, 0, st>>>((const T*)x, (T*)y, rows, cols, scale); break;
+      default: softmax_rows_reg_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)x, (T*)y, rows, cols, scale); break;
+    }
+    return mudiff_launch_status();
+  }
+  size_t smem = sizeof(float) * (size_t)cols;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(softmax_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  softmax_rows_kernel<T><<<grid, 256, smem, st>>>((const T*)x, (T*)y, rows, cols, scale);
+  return mudiff_launch_status();
 }
 
 }  // namespace
@@ -432,18 +488,11 @@ extern "C" int mudiff_pixelnorm(const float* z, float* out, int batch, int dim, 
 
 extern "C" int mudiff_softmax_rows(const void* x, void* y, int dtype, int64_t rows, int cols, float scale, void* stream) {
   if (rows <= 0 || cols <= 0) return rows == 0 ? 0 : MUDIFF_EINVAL;
-  if (cols > 48 * 1024 / 4 * 4) return MUDIFF_EUNSUPPORTED;      // row staged in <= 192 KB smem
+  if (cols > 49152) return MUDIFF_EUNSUPPORTED;      // generic path stages the row in <= 192 KB smem
   cudaStream_t st = (cudaStream_t)stream;
-  size_t smem = sizeof(float) * (size_t)cols;
-  int grid = (int)(rows < MUDIFF_NUM_SMS * 8 ? rows : MUDIFF_NUM_SMS * 8);
-  if (dtype == MUDIFF_F32) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(softmax_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    softmax_rows_kernel<float><<<grid, 256, smem, st>>>((const float*)x, (float*)y, rows, cols, scale);
-  } else if (dtype == MUDIFF_BF16) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(softmax_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    softmax_rows_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, rows, cols, scale);
-  } else return MUDIFF_EUNSUPPORTED;
-  return mudiff_launch_status();
+  if (dtype == MUDIFF_F32) return launch_softmax<float>(x, y, rows, cols, scale, st);
+  if (dtype == MUDIFF_BF16) return launch_softmax<__nv_bfloat16>(x, y, rows, cols, scale, st);
+  return MUDIFF_EUNSUPPORTED;
 }
 
 extern "C" int mudiff_zero(void* p, int64_t nbytes, void* stream) {

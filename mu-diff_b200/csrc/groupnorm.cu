@@ -12,11 +12,17 @@ namespace {
 // Deterministic and batch-invariant: a block always owns GN_PPB consecutive pixels of one image,
 // threads reduce in a fixed order, block partials go to `partial[b][chunk][g]` and the LAST block of
 // each image (self-resetting ticket counter) adds them up in chunk order.  No floating-point atomics.
-#define GN_PPB 512
+// pixels per block: a function of (hw, C) only (=> batch-invariant): ~256 KB of bf16 per block, at least
+// 32 blocks per image for large images
+static inline int gn_ppb(int64_t hw, int C) {
+  int64_t a = 131072 / C; if (a < 256) a = 256;
+  int64_t b = hw / 32; if (b < 256) b = 256;
+  return (int)(a < b ? a : b);
+}
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const T* __restrict__ x1, int c1, int ld1,
                                 int64_t hw, int groups, double* __restrict__ stats, double* __restrict__ partial,
-                                unsigned int* __restrict__ tickets) {
+                                unsigned int* __restrict__ tickets, int GN_PPB) {
   constexpr int V = 16 / sizeof(T);
   const int C = c0 + c1;
   const int cv = C / V;
@@ -203,6 +209,7 @@ int launch_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld
   int block = (256 / cv) * cv;
   if (block < cv) block = cv;                // cv <= 256 since C <= 1024, V >= 4
   const int lanes = block / cv;
+  const int GN_PPB = gn_ppb(hw, C);
   int chunks = (int)((hw + GN_PPB - 1) / GN_PPB);
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
@@ -211,7 +218,7 @@ int launch_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld
   dim3 grid(chunks, batch);
   size_t smem = sizeof(float) * 2 * (size_t)lanes * C;
   gn_stats_kernel<T><<<grid, block, smem, st>>>((const T*)x0, c0, ld0, (const T*)x1, c1, ld1, hw, groups, stats,
-                                               g_scratch[dev].partial, g_scratch[dev].tickets);
+                                               g_scratch[dev].partial, g_scratch[dev].tickets, GN_PPB);
   return mudiff_launch_status();
 }
 
