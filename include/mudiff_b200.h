@@ -88,16 +88,23 @@ int mudiff_posterior_update(const float* x01, int64_t x01_bstride, const float* 
  * Input is the channel-concatenation of up to two NHWC tensors (x0: C0 channels with
  * pixel stride ld0, x1: C1 with ld1; x1 may be NULL) - this is torch.cat([h, hs.pop()], 1)
  * of ncsnpp_generator_adagn_feat.py:383 without materialising it.
- * stats: double[B][G][2] = (sum, sum of squares), overwritten by mudiff_gn_stats.  The reduction
- * is deterministic and batch-invariant (fixed 512-pixel blocks, ordered partial sums, no
- * floating-point atomics).  G groups over C0+C1 channels.
+ * Statistics are PER CHANNEL: chstats double[B][st_ld][2] = (sum, sum of squares) over the H*W pixels; a
+ * tensor's statistics are produced either by mudiff_gn_stats (stand-alone pass) or by the epilogue of
+ * the convolution that wrote the tensor (mudiff_conv_desc.stats + mudiff_stats_finalize).  Both are
+ * deterministic and batch-invariant (ordered partial sums, no floating-point atomics).  The apply
+ * kernel derives the group mean / rstd of the (concatenated) input from the per-channel values, so any
+ * grouping and any concat of tensors with known statistics needs no extra pass.
  * apply: y = act(gamma[b,c] * (x-mean)*rstd + beta[b,c]); gamma/beta fp32 with batch
- * stride gb_bstride (0 => shared affine [C]); NULL gamma/beta => 1/0.
+ * stride gb_bstride (0 => shared affine [C]); NULL gamma/beta => 1/0.  G groups over C0+C1 channels.
  * ------------------------------------------------------------------------------- */
-int mudiff_gn_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int dtype,
-                    int batch, int64_t hw, int groups, double* stats, void* stream);
-int mudiff_gn_apply(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int dtype_in,
-                    const double* stats, const float* gamma, const float* beta, int64_t gb_bstride,
+int mudiff_gn_stats(const void* x, int c, int ld, int dtype, int batch, int64_t hw,
+                    double* chstats, int st_ld, int st_off, void* stream);
+/* partial float[batch*tiles_per_image][n][2] (written by mudiff_conv_tc) -> chstats[b][st_off + c][2] */
+int mudiff_stats_finalize(const float* partial, int tiles_per_image, int n, double* chstats, int st_ld,
+                          int st_off, int batch, void* stream);
+int mudiff_gn_apply(const void* x0, int c0, int ld0, const double* st0, int st0_ld,
+                    const void* x1, int c1, int ld1, const double* st1, int st1_ld, int dtype_in,
+                    const float* gamma, const float* beta, int64_t gb_bstride,
                     void* out, int ld_out, int dtype_out, int batch, int64_t hw, int groups,
                     float eps, int act, void* stream);
 int mudiff_zero(void* p, int64_t nbytes, void* stream);
@@ -142,15 +149,20 @@ typedef struct mudiff_conv_desc {
   void* out;
   int32_t out_ld, out_coff;
   int32_t out_dtype;
-  double* stats;           /* optional fused GroupNorm statistics of the OUTPUT    */
-  int32_t stats_groups;    /*   (sum,sumsq)[batch][groups], accumulated; or NULL   */
-  int32_t flags;           /* bit0: force halo mode, bit1: forbid halo mode,
-                              bit2: descriptor base-offset variant (debug)         */
+  void* stats;             /* optional (mudiff_conv_tc, n <= 256): float partial    */
+  int32_t stats_groups;    /*   [batch*tiles_per_image][n][2] per-tile per-channel  */
+                           /*   (sum,sumsq) of the OUTPUT; stats_groups is unused   */
+  int32_t flags;           /* debug/ablation: bit1 forbid halo staging, bit2 descriptor
+                              base-offset variant, bit3 forbid stationary weights,
+                              bit4 one pixel tile per unit                          */
 } mudiff_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit GEMM (bf16 in, fp32 accumulate).  Requires a_c[i] % 64 == 0,
  * n % 32 == 0, stride == 1.  Returns MUDIFF_EUNSUPPORTED otherwise. */
 int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream);
+/* Planning only: out[0..9] = tile_h, tile_w, tiles_per_image, n_tile, tiles_per_unit, stationary_weights,
+ * a_slots, b_slots, accumulator_stages, halo(seg0).  Callers size `stats` with out[2]. */
+int mudiff_conv_tc_query(const mudiff_conv_desc* d, int32_t* out);
 /* CUDA-core implicit GEMM (fp32 or bf16 storage, fp32 math): any shape, stride 1/2.
  * This is the fp32-parity path and the path for Cin=1 / Cout=1 / strided convs. */
 int mudiff_conv_simt(const mudiff_conv_desc* d, int dtype, void* stream);

@@ -214,16 +214,18 @@ class _NCSNppBase(nn.Module, layers.PackCache):
         nf = self.nf
         b, _, h, w = x.shape
         h0 = ops.empty_nhwc(b, self.stem_c, h, w, dt, x.device)
+        cs0 = torch.empty((b, self.stem_c, 2), dtype=torch.float64, device=x.device)   # per-channel GN statistics of h0
+        ops.set_chstats(h0, cs0)
         m_idx = 2
         if not self.adaptive:
             for j, inp in enumerate([x] + list(conds)):
-                modules[m_idx](inp, compute_dtype=dt, out=h0, out_coff=j * nf)
+                modules[m_idx](inp, compute_dtype=dt, out=h0, out_coff=j * nf, stats_out=(cs0, j * nf))
                 m_idx += 1
             return h0, m_idx
         # ---- adaptive (G2): :733-791 -------------------------------------------------
         pseudo_weight = modules[m_idx](pseudo_target, compute_dtype=dt)
         m_idx += 1
-        modules[m_idx](x, compute_dtype=dt, out=h0, out_coff=0)
+        modules[m_idx](x, compute_dtype=dt, out=h0, out_coff=0, stats_out=(cs0, 0))
         m_idx += 1
         nc = self.n_cond
         cf = ops.empty_nhwc(b, nc * nf, h, w, dt, x.device)          # cat(cond1_feat, cond2_feat[, cond3_feat])
@@ -249,6 +251,7 @@ class _NCSNppBase(nn.Module, layers.PackCache):
             g2 = g_all[:, (2 * p + 1) * nf:(2 * p + 2) * nf]
             att = wconv(ops.gate_mul(g1, feats[a]), compute_dtype=dt)
             ops.gate_blend(g2, att, feats[bb], out=h0[:, (1 + p) * nf:(2 + p) * nf])
+        ops.gn_stats(h0[:, nf:], out=(cs0, nf))          # gated features: stand-alone statistics pass
         return h0, m_idx
 
     def _forward(self, x, conds, time_cond, z, pseudo_target=None):

@@ -47,10 +47,12 @@ PROTOTYPES = {
     'mudiff_upfirdn2d': [_P, _P, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'mudiff_fused_bias_act': [_P, _P, _P, _P, _I, _L, _I, _L, _I, _I, _F, _F, _P],
     'mudiff_posterior_update': [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _P, _I, _L, _P],
-    'mudiff_gn_stats': [_P, _I, _I, _P, _I, _I, _I, _I, _L, _I, _P, _P],
-    'mudiff_gn_apply': [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _L, _P, _I, _I, _I, _L, _I, _F, _I, _P],
+    'mudiff_gn_stats': [_P, _I, _I, _I, _I, _L, _P, _I, _I, _P],
+    'mudiff_stats_finalize': [_P, _I, _I, _P, _I, _I, _I, _P],
+    'mudiff_gn_apply': [_P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _I, _I, _I, _L, _I, _F, _I, _P],
     'mudiff_zero': [_P, _L, _P],
     'mudiff_conv_tc': [C.POINTER(ConvDesc), _P],
+    'mudiff_conv_tc_query': [C.POINTER(ConvDesc), C.POINTER(C.c_int32)],
     'mudiff_conv_simt': [C.POINTER(ConvDesc), _I, _P],
     'mudiff_softmax_rows': [_P, _P, _I, _L, _I, _F, _P],
     'mudiff_linear': [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -1,50 +1,51 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a  (bf16 x bf16 -> fp32).
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a  (bf16 x bf16 -> fp32), version 2.
 //
-//   D[128 pixels, n_tile] += A[128 pixels, 64 ch] * W[n_tile, 64 ch]^T        per K block
+//   D[128 pixels, n_tile] += A[128 pixels, 64 ch] * W[n_tile, 64 ch]^T        per (tap, channel block)
 //
-// Persistent, warp-specialised CTA (192 threads, one per SM):
-//   warp 0      TMA producer: NHWC activation boxes (4-D tensor map; conv padding = TMA
-//               out-of-bounds zero fill) + K-major weight boxes (3-D map) into a ring of
-//               128B-swizzled shared-memory stages, mbarrier complete_tx signalling
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x n_tile x 16),
-//               tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / temb row-bias /
-//               alpha / residual / activation -> bf16|fp32 NHWC stores; double-buffered
-//               TMEM accumulators let tile i+1's MMAs overlap tile i's epilogue
-//
-// Two A-staging modes per 3x3 segment:
-//   per-tap : one {64ch, tw, th} box per (tap, channel block); 9x re-read of the input from L2
-//   halo    : one {64ch, tw+2, th+2} box per channel block, the nine taps are nine UMMA
-//             descriptors into the SAME staged tile (start address shifted by whole 128-byte
-//             pixel rows, stride-byte-offset = halo row pitch).  Needs tw == 8 so that one
-//             8-row swizzle atom is one tile row.  Cuts L2->smem traffic for A by 6.25x.
+// Persistent, warp-specialised CTA (224 threads, one per SM), each CTA owns a CONTIGUOUS range of
+// work units (unit = MT consecutive 128-pixel tiles of one image x one N tile):
+//   warp 0      TMA producer for the A ring: NHWC activation boxes through a 4-D tensor map (conv
+//               padding = TMA out-of-bounds zero fill).  3x3 segments are staged as ONE halo box
+//               {64ch, tw+2, th+2} per channel block; the nine taps are nine UMMA descriptors into
+//               that tile (start address shifted by whole 128-byte pixel rows, SBO = halo row pitch).
+//   warp 1      TMA producer for the B ring: K-major weight sub-tiles {64, n_tile} through a 3-D map,
+//               or - when all of K x n_tile fits - ONE stationary load of the whole weight matrix.
+//   warp 2      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x n_tile x 16); one weight
+//               sub-tile feeds the MMAs of all MT pixel tiles before it is released (tcgen05.commit).
+//   warps 3-6   epilogue: tcgen05.ld -> bias / temb row-bias / alpha / residual / activation ->
+//               bf16|fp32 NHWC stores, plus optional per-tile per-channel (sum, sum^2) partials for
+//               the GroupNorm that consumes the output (butterfly shuffles, no atomics -> deterministic).
+// TMEM holds acc_stages x MT accumulators so that unit i+1's MMAs overlap unit i's epilogue.
 #include <cuda.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace {
 
-constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
-constexpr uint32_t kSmemBudget = 225 * 1024;
+constexpr int kMaxSlots = 16;
+constexpr int kThreads = 224;
+constexpr uint32_t kSmemMax = 232448;       // 227 KB opt-in limit per CTA
 
 struct TcParams {
   int batch, H, W;
-  int tile_h, tile_w, tiles_x, tiles_y, tiles_per_img;
-  int n_tiles, n_tile, total_tiles;
+  int tile_h, tile_w, tiles_x, tpi;           // tpi = pixel tiles per image
+  int MT, gpi;                                // tiles per unit, unit groups per image
+  int n_tiles, n_tile, n_total;
+  long long total_units;
   int nseg;
   int seg_cblk[3], seg_taps[3], seg_halo[3], seg_koff[3], seg_c[3];
   int a_batched, w_batched;
-  uint32_t stage_bytes, a_region_bytes, b_sub_bytes;
-  int num_stages;
+  uint32_t a_slot_bytes, b_sub_bytes, off_b, off_stats, off_bar;
+  int a_slots, b_slots, stationary, b_total_subs;
   uint32_t idesc;
-  int acc_stride;       // TMEM columns between the two accumulator stages
-  int tmem_cols;
-  int base_off_variant; // debug: fill descriptor base-offset field from the address
+  int acc_stride, acc_stages, tmem_cols;
+  int base_off_variant;
   // epilogue
   const float* bias; const float* rowbias; int rowbias_ld;
   const void* residual; int res_ld;
   float alpha, beta; int act;
   void* out; int out_ld, out_coff;
+  float* stats_partial;                       // [batch*tpi][n_total][2] or NULL
 };
 
 // ---------------------------------------------------------------------------------
@@ -126,18 +127,48 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
   return d;
 }
 
-struct TileCoord { int b, y0, x0, n0; };
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
-  TileCoord t;
-  int nt = tile % p.n_tiles;
-  int mt = tile / p.n_tiles;
-  t.b = mt / p.tiles_per_img;
-  int r = mt - t.b * p.tiles_per_img;
-  int ty = r / p.tiles_x;
-  t.y0 = ty * p.tile_h;
-  t.x0 = (r - ty * p.tiles_x) * p.tile_w;
+
+struct Unit { int b, r0, count, n0; };
+__device__ __forceinline__ Unit decode_unit(const TcParams& p, long long u) {
+  Unit t;
+  const int nt = (int)(u % p.n_tiles);
+  const long long g = u / p.n_tiles;
+  t.b = (int)(g / p.gpi);
+  const int gi = (int)(g - (long long)t.b * p.gpi);
+  t.r0 = gi * p.MT;
+  t.count = p.tpi - t.r0 < p.MT ? p.tpi - t.r0 : p.MT;
   t.n0 = nt * p.n_tile;
   return t;
+}
+
+// Enumerates the "A groups" of one unit in the order every role walks them:
+//   halo segment    : one group per channel block, 9 weight sub-tiles (taps) each
+//   plain segment   : one group per (tap, channel block), 1 weight sub-tile each
+template <typename F>
+__device__ __forceinline__ void for_each_group(const TcParams& p, F&& f) {
+  for (int s = 0; s < p.nseg; ++s) {
+    if (p.seg_halo[s]) {
+      for (int cb = 0; cb < p.seg_cblk[s]; ++cb) f(s, cb, 0, 9);
+    } else {
+      for (int tap = 0; tap < p.seg_taps[s]; ++tap)
+        for (int cb = 0; cb < p.seg_cblk[s]; ++cb) f(s, cb, tap, 1);
+    }
+  }
+}
+
+// sum over the 32 lanes of 32 per-lane values; lane j ends up with the total of v[j]
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = upper ? v[i] : v[i + n];
+      const float keep = upper ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
 }
 
 template <bool kOutF32>
@@ -147,9 +178,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.num_stages * p.stage_bytes);
-  uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* a_full = (uint64_t*)(smem + p.off_bar);
+  uint64_t* a_empty = a_full + kMaxSlots;
+  uint64_t* b_full = a_empty + kMaxSlots;
+  uint64_t* b_empty = b_full + kMaxSlots;
+  uint64_t* w_full = b_empty + kMaxSlots;
+  uint64_t* tfull_bar = w_full + 1;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
@@ -157,7 +191,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
@@ -165,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (p.nseg > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA1) : "memory");
     if (p.nseg > 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA2) : "memory");
   }
-  if (warp == 1) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -174,173 +210,249 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // contiguous, balanced range of units for this CTA
+  const long long u_begin = (p.total_units * (long long)blockIdx.x) / gridDim.x;
+  const long long u_end = (p.total_units * (long long)(blockIdx.x + 1)) / gridDim.x;
+
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== A producer ===========================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        const int ab = p.a_batched ? t.b : 0;
-        const int wb = p.w_batched ? t.b : 0;
-        for (int s = 0; s < p.nseg; ++s) {
+      uint32_t a_item = 0;
+      for (long long u = u_begin; u < u_end; ++u) {
+        const Unit un = decode_unit(p, u);
+        const int ab = p.a_batched ? un.b : 0;
+        for_each_group(p, [&](int s, int cb, int tap, int nb) {
           const CUtensorMap* mapA = s == 0 ? &mapA0 : (s == 1 ? &mapA1 : &mapA2);
-          const int taps = p.seg_taps[s];
-          const bool halo = p.seg_halo[s] != 0;
-          const int items = halo ? p.seg_cblk[s] : taps * p.seg_cblk[s];
-          for (int it = 0; it < items; ++it) {
-            int tap, cb;
-            if (halo) { tap = 0; cb = it; } else { tap = it / p.seg_cblk[s]; cb = it - tap * p.seg_cblk[s]; }
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-            uint8_t* sb = sa + p.a_region_bytes;
-            if (halo) {
-              const uint32_t a_bytes = (uint32_t)(p.tile_w + 2) * (p.tile_h + 2) * 128u;
-              mbar_expect_tx(&full_bar[stage], a_bytes + 9u * p.b_sub_bytes);
-              tma_load_4d(sa, mapA, &full_bar[stage], cb * 64, t.x0 - 1, t.y0 - 1, ab);
-              for (int j = 0; j < 9; ++j)
-                tma_load_3d(sb + (size_t)j * p.b_sub_bytes, &mapW, &full_bar[stage],
-                            p.seg_koff[s] + j * p.seg_c[s] + cb * 64, t.n0, wb);
+          for (int m = 0; m < un.count; ++m) {
+            const int r = un.r0 + m;
+            const int ty = r / p.tiles_x;
+            const int y0 = ty * p.tile_h, x0 = (r - ty * p.tiles_x) * p.tile_w;
+            const uint32_t slot = a_item % (uint32_t)p.a_slots;
+            const uint32_t par = ((a_item / (uint32_t)p.a_slots) & 1u) ^ 1u;
+            mbar_wait(&a_empty[slot], par);
+            uint8_t* sa = smem + (size_t)slot * p.a_slot_bytes;
+            if (nb == 9) {
+              mbar_expect_tx(&a_full[slot], (uint32_t)(p.tile_w + 2) * (p.tile_h + 2) * 128u);
+              tma_load_4d(sa, mapA, &a_full[slot], cb * 64, x0 - 1, y0 - 1, ab);
             } else {
-              const int dy = taps == 9 ? tap / 3 - 1 : 0;
-              const int dx = taps == 9 ? tap % 3 - 1 : 0;
-              mbar_expect_tx(&full_bar[stage], 128u * 128u + p.b_sub_bytes);
-              tma_load_4d(sa, mapA, &full_bar[stage], cb * 64, t.x0 + dx, t.y0 + dy, ab);
-              tma_load_3d(sb, &mapW, &full_bar[stage], p.seg_koff[s] + tap * p.seg_c[s] + cb * 64, t.n0, wb);
+              const int dy = p.seg_taps[s] == 9 ? tap / 3 - 1 : 0;
+              const int dx = p.seg_taps[s] == 9 ? tap % 3 - 1 : 0;
+              mbar_expect_tx(&a_full[slot], 128u * 128u);
+              tma_load_4d(sa, mapA, &a_full[slot], cb * 64, x0 + dx, y0 + dy, ab);
             }
-            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+            ++a_item;
           }
-        }
+        });
       }
     }
   } else if (warp == 1) {
+    // =========================== B producer ===========================
+    if (lane == 0) {
+      if (p.stationary) {
+        mbar_expect_tx(w_full, (uint32_t)p.b_total_subs * p.b_sub_bytes);
+        for (int i = 0; i < p.b_total_subs; ++i)
+          tma_load_3d(smem + p.off_b + (size_t)i * p.b_sub_bytes, &mapW, w_full, i * 64, 0, 0);
+      } else {
+        uint32_t b_item = 0;
+        for (long long u = u_begin; u < u_end; ++u) {
+          const Unit un = decode_unit(p, u);
+          const int wb = p.w_batched ? un.b : 0;
+          for_each_group(p, [&](int s, int cb, int tap, int nb) {
+            for (int j = 0; j < nb; ++j) {
+              const int tp = nb == 9 ? j : tap;
+              const uint32_t slot = b_item % (uint32_t)p.b_slots;
+              const uint32_t par = ((b_item / (uint32_t)p.b_slots) & 1u) ^ 1u;
+              mbar_wait(&b_empty[slot], par);
+              mbar_expect_tx(&b_full[slot], p.b_sub_bytes);
+              tma_load_3d(smem + p.off_b + (size_t)slot * p.b_sub_bytes, &mapW, &b_full[slot],
+                          p.seg_koff[s] + tp * p.seg_c[s] + cb * 64, un.n0, wb);
+              ++b_item;
+            }
+          });
+        }
+      }
+    }
+  } else if (warp == 2) {
     // =========================== MMA issuer =============================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+      uint32_t a_item = 0, b_item = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const uint32_t smem_base = smem_u32(smem);
+      if (p.stationary) { mbar_wait(w_full, 0); tc_fence_after(); }
+      for (long long u = u_begin; u < u_end; ++u) {
+        const Unit un = decode_unit(p, u);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-        uint32_t accumulate = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const bool halo = p.seg_halo[s] != 0;
-          const int items = halo ? p.seg_cblk[s] : p.seg_taps[s] * p.seg_cblk[s];
-          const int nb = halo ? 9 : 1;
+        bool first = true;
+        for_each_group(p, [&](int s, int cb, int tap, int nb) {
+          const bool halo = nb == 9;
           const uint32_t sbo_a = halo ? (uint32_t)(p.tile_w + 2) * 128u : 1024u;
-          for (int it = 0; it < items; ++it) {
-            mbar_wait(&full_bar[stage], phase);
+          for (int j = 0; j < nb; ++j) {
+            uint32_t sb, bslot = 0;
+            if (p.stationary) {
+              const int ksub = (p.seg_koff[s] + (halo ? j : tap) * p.seg_c[s]) / 64 + cb;
+              sb = smem_base + p.off_b + (uint32_t)ksub * p.b_sub_bytes;
+            } else {
+              bslot = b_item % (uint32_t)p.b_slots;
+              mbar_wait(&b_full[bslot], (b_item / (uint32_t)p.b_slots) & 1u);
+              sb = smem_base + p.off_b + bslot * p.b_sub_bytes;
+            }
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-            const uint32_t sb = sa + p.a_region_bytes;
-            for (int j = 0; j < nb; ++j) {
-              const uint32_t a_off = halo ? (uint32_t)((j / 3) * (p.tile_w + 2) + (j % 3)) * 128u : 0u;
+            const uint32_t a_off = halo ? (uint32_t)((j / 3) * (p.tile_w + 2) + (j % 3)) * 128u : 0u;
+            for (int m = 0; m < un.count; ++m) {
+              const uint32_t it = a_item + (uint32_t)m;
+              const uint32_t aslot = it % (uint32_t)p.a_slots;
+              if (j == 0) { mbar_wait(&a_full[aslot], (it / (uint32_t)p.a_slots) & 1u); tc_fence_after(); }
+              const uint32_t sa = smem_base + aslot * p.a_slot_bytes;
+              const uint32_t d_tmem = tmem_base + (uint32_t)((acc * p.MT + m) * p.acc_stride);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t ad = umma_desc(sa + a_off + k * 32u, sbo_a, p.base_off_variant);
-                const uint64_t bd = umma_desc(sb + (uint32_t)j * p.b_sub_bytes + k * 32u, 1024u, 0);
-                tc_mma_f16(d_tmem, ad, bd, p.idesc, accumulate);
-                accumulate = 1;
+                const uint64_t bd = umma_desc(sb + k * 32u, 1024u, 0);
+                tc_mma_f16(d_tmem, ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
               }
+              if (j == nb - 1) tc_commit(&a_empty[aslot]);      // this A tile is done after its last tap
             }
-            tc_commit(&empty_bar[stage]);          // frees this smem stage when the MMAs retire
-            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+            if (!p.stationary) { tc_commit(&b_empty[bslot]); ++b_item; }
+            first = false;
           }
-        }
-        tc_commit(&tfull_bar[acc]);                // accumulator complete -> epilogue
-        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+          a_item += (uint32_t)un.count;
+        });
+        tc_commit(&tfull_bar[acc]);                // accumulators complete -> epilogue
+        if (p.acc_stages == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
       }
     }
   } else {
     // =========================== epilogue ===============================
     const int q = warp & 3;                        // TMEM lane quadrant this warp may read
-    const int r = q * 32 + lane;                   // accumulator row == pixel within the tile
-    const int ty = r / p.tile_w, tx = r - ty * p.tile_w;
+    const int ew = warp - 3;                       // epilogue warp index 0..3
+    const int et = ew * 32 + lane;                 // epilogue thread index 0..127
+    const int row = q * 32 + lane;                 // accumulator row == pixel within the tile
+    const int ty_in = row / p.tile_w, tx_in = row - ty_in * p.tile_w;
+    float* sstat = (float*)(smem + p.off_stats);   // [4 warps][n_tile][2]
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
-      const int y = t.y0 + ty, x = t.x0 + tx;
-      const bool valid = (y < p.H) && (x < p.W);
-      const int64_t pix = ((int64_t)t.b * p.H + y) * p.W + x;
+    for (long long u = u_begin; u < u_end; ++u) {
+      const Unit un = decode_unit(p, u);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
-      for (int c = 0; c < p.n_tile; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr0 + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (valid) {
-          const int n = t.n0 + c;
+      for (int m = 0; m < un.count; ++m) {
+        const int r = un.r0 + m;
+        const int tyt = r / p.tiles_x;
+        const int y = tyt * p.tile_h + ty_in, x = (r - tyt * p.tiles_x) * p.tile_w + tx_in;
+        const bool valid = (y < p.H) && (x < p.W);
+        const int64_t pix = ((int64_t)un.b * p.H + y) * p.W + x;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.MT + m) * p.acc_stride);
+        for (int c = 0; c < p.n_tile; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr0 + (uint32_t)c, v);
+          tmem_ld_wait();
+          const int n = un.n0 + c;
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
+          if (valid) {
+            if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + n + j);
-          }
-          if (p.rowbias) {
-            const float* rb = p.rowbias + (int64_t)t.b * p.rowbias_ld + n;
+              for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + n + j);
+            }
+            if (p.rowbias) {
+              const float* rb = p.rowbias + (int64_t)un.b * p.rowbias_ld + n;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += __ldg(rb + j);
-          }
+              for (int j = 0; j < 32; ++j) f[j] += __ldg(rb + j);
+            }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
-          if (p.residual) {
-            if (kOutF32) {
-              const float4* rp = reinterpret_cast<const float4*>((const float*)p.residual + pix * p.res_ld + n);
+            for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+            if (p.residual) {
+              if (kOutF32) {
+                const float4* rp = reinterpret_cast<const float4*>((const float*)p.residual + pix * p.res_ld + n);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 rv = rp[j];
-                f[4 * j + 0] = fmaf(p.beta, rv.x, f[4 * j + 0]); f[4 * j + 1] = fmaf(p.beta, rv.y, f[4 * j + 1]);
-                f[4 * j + 2] = fmaf(p.beta, rv.z, f[4 * j + 2]); f[4 * j + 3] = fmaf(p.beta, rv.w, f[4 * j + 3]);
+                for (int j = 0; j < 8; ++j) {
+                  float4 rv = rp[j];
+                  f[4 * j + 0] = fmaf(p.beta, rv.x, f[4 * j + 0]); f[4 * j + 1] = fmaf(p.beta, rv.y, f[4 * j + 1]);
+                  f[4 * j + 2] = fmaf(p.beta, rv.z, f[4 * j + 2]); f[4 * j + 3] = fmaf(p.beta, rv.w, f[4 * j + 3]);
+                }
+              } else {
+                const uint4* rp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.residual + pix * p.res_ld + n);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 raw = rp[j];
+                  const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[8 * j + i] = fmaf(p.beta, __bfloat162float(e[i]), f[8 * j + i]);
+                }
               }
+            }
+            if (p.act == MUDIFF_ACT_SIGMOID) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = sigmoid_f(f[j]);
+            } else if (p.act == MUDIFF_ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+            } else if (p.act == MUDIFF_ACT_TANH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+            }
+            if (kOutF32) {
+              float4* op = reinterpret_cast<float4*>((float*)p.out + pix * p.out_ld + p.out_coff + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             } else {
-              const uint4* rp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.residual + pix * p.res_ld + n);
+              uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)p.out + pix * p.out_ld + p.out_coff + n);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                uint4 raw = rp[j];
-                const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
+                uint4 raw;
+                __nv_bfloat162* e = reinterpret_cast<__nv_bfloat162*>(&raw);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[8 * j + i] = fmaf(p.beta, __bfloat162float(e[i]), f[8 * j + i]);
+                for (int i = 0; i < 4; ++i) e[i] = __floats2bfloat162_rn(f[8 * j + 2 * i], f[8 * j + 2 * i + 1]);
+                op[j] = raw;
+                if (p.stats_partial) {          // statistics of what was actually stored (bf16-rounded)
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 rr = __bfloat1622float2(e[i]);
+                    f[8 * j + 2 * i] = rr.x; f[8 * j + 2 * i + 1] = rr.y;
+                  }
+                }
               }
             }
-          }
-          if (p.act == MUDIFF_ACT_SIGMOID) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = sigmoid_f(f[j]);
-          } else if (p.act == MUDIFF_ACT_SILU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
-          } else if (p.act == MUDIFF_ACT_TANH) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
-          }
-          if (kOutF32) {
-            float4* op = reinterpret_cast<float4*>((float*)p.out + pix * p.out_ld + p.out_coff + n);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } else {
-            uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)p.out + pix * p.out_ld + p.out_coff + n);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 raw;
-              __nv_bfloat162* e = reinterpret_cast<__nv_bfloat162*>(&raw);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) e[i] = __floats2bfloat162_rn(f[8 * j + 2 * i], f[8 * j + 2 * i + 1]);
-              op[j] = raw;
-            }
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
           }
+          if (p.stats_partial) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+            const float cs = warp_transpose_reduce(f, lane);
+            const float cq = warp_transpose_reduce(sq, lane);
+            sstat[((ew * p.n_tile) + c + lane) * 2 + 0] = cs;
+            sstat[((ew * p.n_tile) + c + lane) * 2 + 1] = cq;
+          }
+        }
+        if (p.stats_partial) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float* dst = p.stats_partial + (((int64_t)un.b * p.tpi + r) * p.n_total + un.n0) * 2;
+          for (int col = et; col < p.n_tile; col += 128) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              s0 += sstat[((w * p.n_tile) + col) * 2 + 0];
+              s1 += sstat[((w * p.n_tile) + col) * 2 + 1];
+            }
+            *reinterpret_cast<float2*>(dst + col * 2) = make_float2(s0, s1);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      if (p.acc_stages == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -395,12 +507,14 @@ int make_map_w(CUtensorMap* m, const void* ptr, int ktot, int w_ld, int n, int w
   return r == CUDA_SUCCESS ? 0 : MUDIFF_EINVAL;
 }
 
-}  // namespace
 
-extern "C" int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream) {
+// ---------------------------------------------------------------------------------
+// planning (shared by the launcher and mudiff_conv_tc_query)
+// ---------------------------------------------------------------------------------
+int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   if (!d || d->nseg < 1 || d->nseg > 3 || d->batch <= 0 || d->h <= 0 || d->w <= 0 || d->n <= 0) return MUDIFF_EINVAL;
   if (!d->wt || !d->out) return MUDIFF_EINVAL;
-  if (d->stride != 1 || d->stats) return MUDIFF_EUNSUPPORTED;
+  if (d->stride != 1) return MUDIFF_EUNSUPPORTED;
   if (d->n % 32 || d->out_ld % 8 || d->out_coff % 8 || (d->residual && d->res_ld % 8)) return MUDIFF_EUNSUPPORTED;
   if (d->out_dtype != MUDIFF_BF16 && d->out_dtype != MUDIFF_F32) return MUDIFF_EUNSUPPORTED;
   bool any9 = false;
@@ -411,79 +525,129 @@ extern "C" int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream) {
     any9 |= d->a_taps[s] == 9;
     ktot += d->a_taps[s] * d->a_c[s];
   }
+  ktot_out = ktot;
   if (any9 && d->pad != 1) return MUDIFF_EUNSUPPORTED;
   if (((uintptr_t)d->wt % 16) || ((uintptr_t)d->out % 16) || (d->w_ld % 8) || (d->w_bstride % 8)) return MUDIFF_EUNSUPPORTED;
 
-  TcParams p;
   memset(&p, 0, sizeof(p));
   p.batch = d->batch; p.H = d->h; p.W = d->w;
-  // N tiling: largest multiple of 32 that divides n and is <= 256
   int n_tile = 0;
   for (int c = 256; c >= 32; c -= 32) if (d->n % c == 0) { n_tile = c; break; }
   if (!n_tile) return MUDIFF_EUNSUPPORTED;
-  p.n_tile = n_tile; p.n_tiles = d->n / n_tile;
-  // A staging mode
-  // halo staging by default whenever it applies (N <= 64: the A operand dominates L2->smem traffic)
-  bool want_halo = true;
-  if (d->flags & 2) want_halo = false;
-  if (!any9 || d->w < 8 || d->h < 2 || n_tile > 64) want_halo = false;
-  if (want_halo) { p.tile_w = 8; p.tile_h = 16; }
+  p.n_tile = n_tile; p.n_tiles = d->n / n_tile; p.n_total = d->n;
+  // A staging: halo whenever a 3x3 segment exists and the image is at least one 8x2 patch
+  bool halo = any9 && d->w >= 8 && d->h >= 2 && !(d->flags & 2);
+  if (halo) { p.tile_w = 8; p.tile_h = 16; }
   else if (d->h == 1) { p.tile_w = 128; p.tile_h = 1; }
   else if (d->w >= 16) { p.tile_w = 16; p.tile_h = 8; }
   else { p.tile_w = 8; p.tile_h = 16; }
   p.tiles_x = (d->w + p.tile_w - 1) / p.tile_w;
-  p.tiles_y = (d->h + p.tile_h - 1) / p.tile_h;
-  p.tiles_per_img = p.tiles_x * p.tiles_y;
-  p.total_tiles = p.tiles_per_img * d->batch * p.n_tiles;
+  const int tiles_y = (d->h + p.tile_h - 1) / p.tile_h;
+  p.tpi = p.tiles_x * tiles_y;
   p.nseg = d->nseg;
   p.a_batched = d->a_batched ? 1 : 0;
   p.w_batched = d->w_bstride != 0 ? 1 : 0;
   p.b_sub_bytes = (uint32_t)n_tile * 128u;
-  uint32_t a_region = 128u * 128u;
-  int nb_max = 1;
   int koff = 0;
+  p.a_slot_bytes = 128u * 128u;
   for (int s = 0; s < d->nseg; ++s) {
     p.seg_c[s] = d->a_c[s]; p.seg_cblk[s] = d->a_c[s] / 64; p.seg_taps[s] = d->a_taps[s];
-    p.seg_halo[s] = (want_halo && d->a_taps[s] == 9) ? 1 : 0;
+    p.seg_halo[s] = (halo && d->a_taps[s] == 9) ? 1 : 0;
     p.seg_koff[s] = koff; koff += d->a_taps[s] * d->a_c[s];
     if (p.seg_halo[s]) {
-      uint32_t hb = (uint32_t)(p.tile_w + 2) * (p.tile_h + 2) * 128u;
-      if (hb > a_region) a_region = hb;
-      nb_max = 9;
+      uint32_t hb = ((uint32_t)(p.tile_w + 2) * (p.tile_h + 2) * 128u + 1023u) & ~1023u;
+      if (hb > p.a_slot_bytes) p.a_slot_bytes = hb;
     }
   }
-  p.a_region_bytes = (a_region + 1023u) & ~1023u;
-  p.stage_bytes = p.a_region_bytes + (uint32_t)nb_max * p.b_sub_bytes;   // b_sub_bytes is a multiple of 1024 (n_tile % 8 == 0)
-  p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
-  const uint32_t tail = 1024;   // barriers + tmem slot
-  int stages = (int)((kSmemBudget - tail - 1024) / p.stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return MUDIFF_EUNSUPPORTED;
-  p.num_stages = stages;
+  // TMEM plan: MT tiles per unit x acc_stages accumulator sets
+  int pow2 = 32; while (pow2 < n_tile) pow2 <<= 1;
+  int MT = (p.tpi >= 2 && !(d->flags & 16)) ? 2 : 1;
+  int stages = 2;
+  if (MT * stages * pow2 > 512) {
+    if (n_tile > 128 && n_tile < 256 && p.tpi >= 2 && !(d->flags & 16)) { MT = 2; stages = 1; }   // e.g. n_tile = 192
+    else { MT = 1; stages = 2; }
+  }
+  if (MT * stages * pow2 > 512) stages = 1;
+  if (MT * stages * pow2 > 512) return MUDIFF_EUNSUPPORTED;
+  p.MT = MT; p.acc_stages = stages; p.acc_stride = pow2;
+  int cols = MT * stages * pow2; int tc = 32; while (tc < cols) tc <<= 1;
+  p.tmem_cols = tc;
+  p.gpi = (p.tpi + MT - 1) / MT;
+  p.total_units = (long long)d->batch * p.gpi * p.n_tiles;
+  // shared memory plan
+  const uint32_t bar_bytes = 1024;
+  const uint32_t stats_bytes = d->stats ? (uint32_t)n_tile * 32u : 0u;
+  const uint32_t fixed = bar_bytes + ((stats_bytes + 1023u) & ~1023u) + 1024u /*alignment slack*/;
+  const uint32_t avail = kSmemMax - fixed;
+  const uint32_t b_total = (uint32_t)(ktot / 64) * p.b_sub_bytes;
+  const int a_min = 2 * MT;
+  p.stationary = 0;
+  if (p.n_tiles == 1 && !p.w_batched && !(d->flags & 8) && (d->w_ld == 0 || d->w_ld == ktot) &&
+      b_total + (uint32_t)a_min * p.a_slot_bytes <= avail && b_total < (1u << 20)) {
+    p.stationary = 1;
+    p.b_total_subs = ktot / 64;
+    int as = (int)((avail - b_total) / p.a_slot_bytes);
+    p.a_slots = as > 8 ? 8 : as;
+    p.b_slots = 0;
+    p.off_b = (uint32_t)p.a_slots * p.a_slot_bytes;
+    p.off_stats = p.off_b + b_total;
+  } else {
+    p.a_slots = a_min;
+    int bs = (int)((avail - (uint32_t)a_min * p.a_slot_bytes) / p.b_sub_bytes);
+    if (bs < 2) {                       // not enough room: fall back to fewer A slots
+      if (MT == 2) return MUDIFF_EUNSUPPORTED;
+      return MUDIFF_EUNSUPPORTED;
+    }
+    if (bs > 12) {                      // spend the surplus on a deeper A ring
+      int extra = (int)(((uint32_t)(bs - 12) * p.b_sub_bytes) / p.a_slot_bytes);
+      p.a_slots += extra; if (p.a_slots > 8) p.a_slots = 8;
+      bs = 12;
+    }
+    p.b_slots = bs;
+    p.off_b = (uint32_t)p.a_slots * p.a_slot_bytes;
+    p.off_stats = p.off_b + (uint32_t)bs * p.b_sub_bytes;
+  }
+  p.off_bar = p.off_stats + ((stats_bytes + 1023u) & ~1023u);
+  if (p.off_bar + bar_bytes + 1024u > kSmemMax) return MUDIFF_EUNSUPPORTED;
   // UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, N = n_tile, M = 128
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((128u >> 4) << 24);
-  p.acc_stride = n_tile <= 64 ? 64 : (n_tile <= 128 ? 128 : 256);
-  p.tmem_cols = 2 * p.acc_stride;
   p.base_off_variant = (d->flags & 4) ? 1 : 0;
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
   p.residual = d->residual; p.res_ld = d->res_ld; p.alpha = d->alpha; p.beta = d->beta; p.act = d->act;
   p.out = d->out; p.out_ld = d->out_ld; p.out_coff = d->out_coff;
+  p.stats_partial = (float*)d->stats;
+  return 0;
+}
 
+}  // namespace
+
+extern "C" int mudiff_conv_tc_query(const mudiff_conv_desc* d, int32_t* out) {
+  TcParams p; int ktot = 0;
+  int rc = plan_conv(d, p, ktot);
+  if (rc) return rc;
+  out[0] = p.tile_h; out[1] = p.tile_w; out[2] = p.tpi; out[3] = p.n_tile; out[4] = p.MT;
+  out[5] = p.stationary; out[6] = p.a_slots; out[7] = p.b_slots; out[8] = p.acc_stages; out[9] = p.seg_halo[0];
+  return 0;
+}
+
+extern "C" int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream) {
+  TcParams p; int ktot = 0;
+  int rc = plan_conv(d, p, ktot);
+  if (rc) return rc;
   CUtensorMap maps[3], mapw;
   memset(maps, 0, sizeof(maps));
   for (int s = 0; s < 3; ++s) {
     int ss = s < d->nseg ? s : 0;
     int bw = p.seg_halo[ss] ? p.tile_w + 2 : p.tile_w;
     int bh = p.seg_halo[ss] ? p.tile_h + 2 : p.tile_h;
-    int rc = make_map_a(&maps[s], d->a[ss], d->a_c[ss], d->a_ld[ss], d->w, d->h, d->a_batched ? d->batch : 1, bw, bh);
+    rc = make_map_a(&maps[s], d->a[ss], d->a_c[ss], d->a_ld[ss], d->w, d->h, d->a_batched ? d->batch : 1, bw, bh);
     if (rc) return rc;
   }
-  {
-    int rc = make_map_w(&mapw, d->wt, ktot, d->w_ld > 0 ? d->w_ld : ktot, d->n, p.w_batched ? d->batch : 1, d->w_bstride, n_tile);
-    if (rc) return rc;
-  }
-  const size_t smem_bytes = (size_t)stages * p.stage_bytes + tail + 1024;
-  int grid = p.total_tiles < MUDIFF_NUM_SMS ? p.total_tiles : MUDIFF_NUM_SMS;
+  rc = make_map_w(&mapw, d->wt, ktot, d->w_ld > 0 ? d->w_ld : ktot, d->n, p.w_batched ? d->batch : 1, d->w_bstride, p.n_tile);
+  if (rc) return rc;
+  const size_t smem_bytes = (size_t)p.off_bar + 1024 + 1024;
+  long long g = p.total_units < MUDIFF_NUM_SMS ? p.total_units : MUDIFF_NUM_SMS;
+  const int grid = (int)g;
   cudaStream_t st = (cudaStream_t)stream;
   // opt in to the full 227 KB of dynamic shared memory once per kernel instantiation (per device)
   static bool attr_set[16][2] = {};
@@ -491,8 +655,8 @@ extern "C" int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream) {
   if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
   const int which = d->out_dtype == MUDIFF_F32 ? 1 : 0;
   if (!attr_set[dev][which]) {
-    cudaError_t e = which ? cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)
-                          : cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = which ? cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)
+                          : cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev][which] = true;
   }

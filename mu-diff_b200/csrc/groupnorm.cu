@@ -21,8 +21,8 @@ static inline int gn_ppb(int64_t hw, int C) {
 }
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const T* __restrict__ x1, int c1, int ld1,
-                                int64_t hw, int groups, double* __restrict__ stats, double* __restrict__ partial,
-                                unsigned int* __restrict__ tickets, int GN_PPB) {
+                                int64_t hw, int groups, double* __restrict__ stats, int st_ld, int st_off,
+                                double* __restrict__ partial, unsigned int* __restrict__ tickets, int GN_PPB) {
   constexpr int V = 16 / sizeof(T);
   const int C = c0 + c1;
   const int cv = C / V;
@@ -92,7 +92,7 @@ __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const
   for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
     double a = 0.0;
     for (int k = 0; k < chunks; ++k) a += pb[(int64_t)k * groups * 2 + i];
-    stats[(int64_t)b * groups * 2 + i] = a;
+    stats[((int64_t)b * st_ld + st_off) * 2 + i] = a;
   }
 }
 
@@ -101,33 +101,45 @@ __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const
 #define GN_APPLY_PPB 1024
 template <typename TI, typename TO>
 __global__ void gn_apply_kernel(const TI* __restrict__ x0, int c0, int ld0, const TI* __restrict__ x1, int c1, int ld1,
-                                const double* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int64_t gb_bstride, TO* __restrict__ out, int ld_out,
-                                int64_t hw, int groups, float eps, int act) {
+                                const double* __restrict__ st0, int st0_ld, const double* __restrict__ st1, int st1_ld,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int64_t gb_bstride,
+                                TO* __restrict__ out, int ld_out, int64_t hw, int groups, float eps, int act) {
   // vector width is chosen on the WIDER of the two element types so both sides stay <= 16 bytes
   constexpr int V = (sizeof(TI) >= sizeof(TO)) ? 16 / sizeof(TI) : 16 / sizeof(TO);
   const int C = c0 + c1;
   const int cv = C / V;
   const int b = blockIdx.y;
+  const int cpg = C / groups;
+  __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
+  // per-channel (sum, sumsq) of the two sources -> per-group mean / rstd (double math, once per block)
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double a = 0.0, q = 0.0;
+    for (int i = 0; i < cpg; ++i) {
+      const int c = g * cpg + i;
+      const double* sp = c < c0 ? st0 + ((int64_t)b * st0_ld + c) * 2 : st1 + ((int64_t)b * st1_ld + (c - c0)) * 2;
+      a += sp[0]; q += sp[1];
+    }
+    const double cnt = (double)hw * (double)cpg;
+    const double m = a / cnt;
+    double var = q / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)m;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
   const int my_cv = threadIdx.x % cv;
   const int lane = threadIdx.x / cv;
   const int lanes = blockDim.x / cv;
   const int ch = my_cv * V;
-  const int cpg = C / groups;
-  const double cnt = (double)hw * (double)cpg;
   float sc[V], sh[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) {
     const int c = ch + k;
     const int g = c / cpg;
-    const double m = stats[((int64_t)b * groups + g) * 2 + 0] / cnt;
-    double var = stats[((int64_t)b * groups + g) * 2 + 1] / cnt - m * m;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const float ga = gamma ? gamma[(int64_t)b * gb_bstride + c] : 1.f;
     const float be = beta ? beta[(int64_t)b * gb_bstride + c] : 0.f;
-    sc[k] = ga * rstd;
-    sh[k] = be - (float)m * sc[k];
+    sc[k] = ga * s_rstd[g];
+    sh[k] = be - s_mean[g] * sc[k];
   }
   const TI* src; int ld;
   if (ch < c0) { src = x0 + (int64_t)b * hw * ld0 + ch; ld = ld0; }
@@ -171,6 +183,25 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x0, int c0, int ld0, cons
   }
 }
 
+// Per-tile per-channel (sum, sumsq) float partials written by the conv epilogue -> per-channel doubles.
+// One block per image, ordered summation over the tiles (deterministic, batch-invariant).
+__global__ void stats_finalize_kernel(const float* __restrict__ partial, int tpi, int n, double* __restrict__ chstats,
+                                      int st_ld, int st_off) {
+  const int b = blockIdx.x;
+  const float* pb = partial + (int64_t)b * tpi * n * 2;
+  for (int i = threadIdx.x; i < n * 2; i += blockDim.x) {
+    double a = 0.0;
+    int t = 0;
+    for (; t + 4 <= tpi; t += 4) {
+      const float v0 = pb[(int64_t)(t + 0) * n * 2 + i], v1 = pb[(int64_t)(t + 1) * n * 2 + i];
+      const float v2 = pb[(int64_t)(t + 2) * n * 2 + i], v3 = pb[(int64_t)(t + 3) * n * 2 + i];
+      a += (double)v0; a += (double)v1; a += (double)v2; a += (double)v3;
+    }
+    for (; t < tpi; ++t) a += (double)pb[(int64_t)t * n * 2 + i];
+    chstats[((int64_t)b * st_ld + st_off) * 2 + i] = a;
+  }
+}
+
 // scratch for block partials + ticket counters, grown on demand (single stream of use per device)
 struct StatsScratch { double* partial = nullptr; size_t cap = 0; unsigned int* tickets = nullptr; int tcap = 0; };
 static StatsScratch g_scratch[16];
@@ -200,7 +231,7 @@ static int ensure_scratch(int dev, size_t need_partial, int need_tickets, cudaSt
 
 template <typename T>
 int launch_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int batch, int64_t hw,
-                 int groups, double* stats, cudaStream_t st) {
+                 int groups, double* stats, int st_ld, int st_off, cudaStream_t st) {
   constexpr int V = 16 / sizeof(T);
   const int C = c0 + c1;
   if (C % V || c0 % V || ld0 % V || (x1 && ld1 % V) || C > GN_MAX_C || C % groups) return MUDIFF_EUNSUPPORTED;
@@ -217,26 +248,27 @@ int launch_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld
   if (rc) return rc;
   dim3 grid(chunks, batch);
   size_t smem = sizeof(float) * 2 * (size_t)lanes * C;
-  gn_stats_kernel<T><<<grid, block, smem, st>>>((const T*)x0, c0, ld0, (const T*)x1, c1, ld1, hw, groups, stats,
+  gn_stats_kernel<T><<<grid, block, smem, st>>>((const T*)x0, c0, ld0, (const T*)x1, c1, ld1, hw, groups, stats, st_ld, st_off,
                                                g_scratch[dev].partial, g_scratch[dev].tickets, GN_PPB);
   return mudiff_launch_status();
 }
 
 template <typename TI, typename TO>
-int launch_apply(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, const double* stats,
-                 const float* gamma, const float* beta, int64_t gbs, void* out, int ld_out, int batch, int64_t hw,
-                 int groups, float eps, int act, cudaStream_t st) {
+int launch_apply(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, const double* st0, int st0_ld,
+                 const double* st1, int st1_ld, const float* gamma, const float* beta, int64_t gbs, void* out,
+                 int ld_out, int batch, int64_t hw, int groups, float eps, int act, cudaStream_t st) {
   constexpr int V = (sizeof(TI) >= sizeof(TO)) ? 16 / sizeof(TI) : 16 / sizeof(TO);
   const int C = c0 + c1;
-  if (C % V || c0 % V || ld0 % V || (x1 && ld1 % V) || ld_out % V || C > GN_MAX_C || C % groups) return MUDIFF_EUNSUPPORTED;
+  if (C % V || c0 % V || ld0 % V || (x1 && ld1 % V) || ld_out % V || C > GN_MAX_C || C % groups || groups > GN_MAX_C / 4)
+    return MUDIFF_EUNSUPPORTED;
   if (((uintptr_t)x0 % 16) || (x1 && ((uintptr_t)x1 % 16)) || ((uintptr_t)out % 16)) return MUDIFF_EUNSUPPORTED;
   const int cv = C / V;
   int block = (256 / cv) * cv;
   if (block < cv) block = cv;
   int chunks = (int)((hw + GN_APPLY_PPB - 1) / GN_APPLY_PPB);
   dim3 grid(chunks, batch);
-  gn_apply_kernel<TI, TO><<<grid, block, 0, st>>>((const TI*)x0, c0, ld0, (const TI*)x1, c1, ld1, stats, gamma, beta, gbs,
-                                                  (TO*)out, ld_out, hw, groups, eps, act);
+  gn_apply_kernel<TI, TO><<<grid, block, 0, st>>>((const TI*)x0, c0, ld0, (const TI*)x1, c1, ld1, st0, st0_ld, st1, st1_ld,
+                                                  gamma, beta, gbs, (TO*)out, ld_out, hw, groups, eps, act);
   return mudiff_launch_status();
 }
 
@@ -267,8 +299,8 @@ extern "C" int mudiff_gap(const void* x, int ld, int dtype, float* out, int batc
     gap_stats[dev] = p; gap_cap[dev] = cap;
   }
   int rc;
-  if (dtype == MUDIFF_F32) rc = launch_stats<float>(x, c, ld, nullptr, 0, 0, batch, hw, c, gap_stats[dev], st);
-  else if (dtype == MUDIFF_BF16) rc = launch_stats<__nv_bfloat16>(x, c, ld, nullptr, 0, 0, batch, hw, c, gap_stats[dev], st);
+  if (dtype == MUDIFF_F32) rc = launch_stats<float>(x, c, ld, nullptr, 0, 0, batch, hw, c, gap_stats[dev], c, 0, st);
+  else if (dtype == MUDIFF_BF16) rc = launch_stats<__nv_bfloat16>(x, c, ld, nullptr, 0, 0, batch, hw, c, gap_stats[dev], c, 0, st);
   else return MUDIFF_EUNSUPPORTED;
   if (rc) return rc;
   int n = batch * c;
@@ -276,27 +308,35 @@ extern "C" int mudiff_gap(const void* x, int ld, int dtype, float* out, int batc
   return mudiff_launch_status();
 }
 
-extern "C" int mudiff_gn_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int dtype,
-                               int batch, int64_t hw, int groups, double* stats, void* stream) {
-  if (batch <= 0 || hw <= 0 || groups <= 0 || c0 <= 0 || c1 < 0 || !x0 || !stats) return MUDIFF_EINVAL;
-  if (!x1) c1 = 0;
+extern "C" int mudiff_gn_stats(const void* x, int c, int ld, int dtype, int batch, int64_t hw,
+                               double* chstats, int st_ld, int st_off, void* stream) {
+  if (batch <= 0 || hw <= 0 || c <= 0 || !x || !chstats || st_ld < c + st_off) return MUDIFF_EINVAL;
   if (batch > 65535) return MUDIFF_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == MUDIFF_F32) return launch_stats<float>(x0, c0, ld0, x1, c1, ld1, batch, hw, groups, stats, st);
-  if (dtype == MUDIFF_BF16) return launch_stats<__nv_bfloat16>(x0, c0, ld0, x1, c1, ld1, batch, hw, groups, stats, st);
+  if (dtype == MUDIFF_F32) return launch_stats<float>(x, c, ld, nullptr, 0, 0, batch, hw, c, chstats, st_ld, st_off, st);
+  if (dtype == MUDIFF_BF16) return launch_stats<__nv_bfloat16>(x, c, ld, nullptr, 0, 0, batch, hw, c, chstats, st_ld, st_off, st);
   return MUDIFF_EUNSUPPORTED;
 }
 
-extern "C" int mudiff_gn_apply(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, int dtype_in,
-                               const double* stats, const float* gamma, const float* beta, int64_t gb_bstride,
+extern "C" int mudiff_stats_finalize(const float* partial, int tiles_per_image, int n, double* chstats, int st_ld,
+                                     int st_off, int batch, void* stream) {
+  if (!partial || !chstats || tiles_per_image <= 0 || n <= 0 || batch <= 0 || st_ld < n + st_off) return MUDIFF_EINVAL;
+  stats_finalize_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(partial, tiles_per_image, n, chstats, st_ld, st_off);
+  return mudiff_launch_status();
+}
+
+extern "C" int mudiff_gn_apply(const void* x0, int c0, int ld0, const double* st0, int st0_ld,
+                               const void* x1, int c1, int ld1, const double* st1, int st1_ld, int dtype_in,
+                               const float* gamma, const float* beta, int64_t gb_bstride,
                                void* out, int ld_out, int dtype_out, int batch, int64_t hw, int groups,
                                float eps, int act, void* stream) {
-  if (batch <= 0 || hw <= 0 || groups <= 0 || c0 <= 0 || c1 < 0 || !x0 || !stats || !out) return MUDIFF_EINVAL;
+  if (batch <= 0 || hw <= 0 || groups <= 0 || c0 <= 0 || c1 < 0 || !x0 || !st0 || !out) return MUDIFF_EINVAL;
   if (act != MUDIFF_ACT_NONE && act != MUDIFF_ACT_SILU) return MUDIFF_EINVAL;
   if (!x1) c1 = 0;
+  if (c1 > 0 && !st1) return MUDIFF_EINVAL;
   if (batch > 65535) return MUDIFF_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-#define AP(TI, TO) return launch_apply<TI, TO>(x0, c0, ld0, x1, c1, ld1, stats, gamma, beta, gb_bstride, out, ld_out, batch, hw, groups, eps, act, st)
+#define AP(TI, TO) return launch_apply<TI, TO>(x0, c0, ld0, x1, c1, ld1, st0, st0_ld, st1, st1_ld, gamma, beta, gb_bstride, out, ld_out, batch, hw, groups, eps, act, st)
   if (dtype_in == MUDIFF_F32 && dtype_out == MUDIFF_F32) AP(float, float);
   if (dtype_in == MUDIFF_BF16 && dtype_out == MUDIFF_BF16) AP(__nv_bfloat16, __nv_bfloat16);
   if (dtype_in == MUDIFF_F32 && dtype_out == MUDIFF_BF16) AP(float, __nv_bfloat16);

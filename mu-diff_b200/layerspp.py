@@ -56,9 +56,8 @@ class AdaptiveGroupNorm(nn.Module):
         L.require_cuda(*srcs)
         gb = self.style_params(style) if gb is None else gb
         c = self.in_channel
-        stats = ops.gn_stats(srcs, self.num_groups)
-        return ops.gn_apply(srcs, stats, self.num_groups, gamma=gb, beta=gb[:, c:], gb_bstride=gb.stride(0),
-                            eps=self.norm.eps, act=act)
+        return ops.gn_apply(srcs, [ops.get_chstats(t) for t in srcs], self.num_groups, gamma=gb, beta=gb[:, c:],
+                            gb_bstride=gb.stride(0), eps=self.norm.eps, act=act)
 
 
 class GroupNorm_Conv(nn.Module):
@@ -156,7 +155,7 @@ class AttnBlockpp(nn.Module, layers.PackCache):
         o = ops.conv([(s, 1)], vt, C, pad=0, w_bstride=C * Lt, w_ld=Lt)   # [B,C,1,L]
         o = o.permute(0, 2, 3, 1).reshape(B, H, W, C).permute(0, 3, 1, 2)
         sc = ops.SQRT2_INV if self.skip_rescale else 1.0
-        return ops.conv([(o, 1)], w_o, C, bias=b_o, pad=0, residual=x, alpha=sc, beta=sc)
+        return ops.conv([(o, 1)], w_o, C, bias=b_o, pad=0, residual=x, alpha=sc, beta=sc, want_stats=True)
 
 
 class Upsample(nn.Module):
@@ -259,7 +258,7 @@ class ResnetBlockBigGANpp_Adagn(nn.Module, layers.PackCache):
         if tbias is None and temb is not None:
             tbias = ops.linear(temb, self.Dense_0.weight, self.Dense_0.bias, act_in=L.ACT_SILU)
         h = ops.conv([(h, 9)], self.Conv_0.packed_weight(dt), self.out_ch, bias=self.Conv_0.bias_f32(),
-                     rowbias=tbias)
+                     rowbias=tbias, want_stats=True)
         h = self.GroupNorm_1(h, zemb, act=L.ACT_SILU, gb=gb1)
         sc = ops.SQRT2_INV if self.skip_rescale else 1.0
         w1 = self.Conv_1.packed_weight(dt)
@@ -270,9 +269,10 @@ class ResnetBlockBigGANpp_Adagn(nn.Module, layers.PackCache):
                               lambda: torch.cat([w1, c2.packed_weight(dt, seg_c)], dim=1).contiguous())
             bias = self._packed(('b12',), [self.Conv_1.bias, c2.bias],
                                 lambda: (self.Conv_1.bias + c2.bias).detach().float().contiguous())
-            return ops.conv([(h, 9)] + [(t, 1) for t in xs], wt, self.out_ch, bias=bias, alpha=sc)
+            return ops.conv([(h, 9)] + [(t, 1) for t in xs], wt, self.out_ch, bias=bias, alpha=sc, want_stats=True)
         res = xs[0] if len(xs) == 1 else ops.concat(xs)
-        return ops.conv([(h, 9)], w1, self.out_ch, bias=self.Conv_1.bias_f32(), residual=res, alpha=sc, beta=sc)
+        return ops.conv([(h, 9)], w1, self.out_ch, bias=self.Conv_1.bias_f32(), residual=res, alpha=sc, beta=sc,
+                        want_stats=True)
 
 
 class ConvFeatBlock(nn.Module):
@@ -285,11 +285,11 @@ class ConvFeatBlock(nn.Module):
         self.act = act
         self.conv2 = conv3x3(out_ch, out_ch)
 
-    def forward(self, x, compute_dtype=None, out=None, out_coff=0):
+    def forward(self, x, compute_dtype=None, out=None, out_coff=0, stats_out=None):
         dt = compute_dtype or _compute_dtype(x)
-        h = self.conv1(x, compute_dtype=dt)
+        h = self.conv1(x, compute_dtype=dt, want_stats=True)
         h = self.group_norm(h, act=L.ACT_SILU)
-        return self.conv2(h, compute_dtype=dt, out=out, out_coff=out_coff)
+        return self.conv2(h, compute_dtype=dt, out=out, out_coff=out_coff, want_stats=True, stats_out=stats_out)
 
 
 class ConvBlock(nn.Module):
@@ -304,7 +304,7 @@ class ConvBlock(nn.Module):
 
     def forward(self, x, style=None, compute_dtype=None, out=None, out_coff=0):
         dt = compute_dtype or _compute_dtype(x)
-        h = self.conv1(x, compute_dtype=dt)
+        h = self.conv1(x, compute_dtype=dt, want_stats=True)
         h = self.group_norm(h, style, act=L.ACT_SILU)
         return self.conv2(h, compute_dtype=dt, out=out, out_coff=out_coff)
 
@@ -323,7 +323,7 @@ class ConvBlock_GAP(nn.Module):
 
     def forward(self, x, compute_dtype=None):
         dt = compute_dtype or _compute_dtype(x)
-        h = self.conv1(x, compute_dtype=dt)
+        h = self.conv1(x, compute_dtype=dt, want_stats=True)
         h = self.group_norm(h, act=L.ACT_SILU)
         h = self.conv2(h, compute_dtype=dt)
         g = ops.gap(h)

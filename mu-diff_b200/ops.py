@@ -123,35 +123,58 @@ def upfirdn2d_nhwc(x, kernel_f32, up=1, down=1, pad=(0, 0)):
 
 
 # ---------------------------------------------------------------------------------
-# GroupNorm
+# GroupNorm.  Statistics travel with the tensors as per-channel (sum, sumsq) doubles [B, C, 2]
+# (attribute `_mudiff_chstats`), produced by the conv epilogue or by the stand-alone stats kernel.
 # ---------------------------------------------------------------------------------
-def gn_stats(srcs, groups):
-    """srcs: 1 or 2 channels-last tensors (channel concat). returns double [B,G,2]."""
-    x0 = srcs[0]
-    x1 = srcs[1] if len(srcs) > 1 else None
-    b, c0, h, w = x0.shape
-    stats = torch.empty((b, groups, 2), dtype=torch.float64, device=x0.device)
-    rc = L.lib().mudiff_gn_stats(x0.data_ptr(), c0, _pix_ld(x0),
-                                 x1.data_ptr() if x1 is not None else None,
-                                 x1.shape[1] if x1 is not None else 0, _pix_ld(x1) if x1 is not None else 0,
-                                 L.dtype_code(x0.dtype), b, h * w, groups, stats.data_ptr(), L.stream_ptr(x0.device))
+_CHSTATS = '_mudiff_chstats'
+
+
+def gn_stats(x, out=None):
+    """Per-channel (sum, sumsq) of a channels-last tensor -> double [B, C, 2] (or into out=(buf, coff))."""
+    x = as_nhwc(x)
+    b, c, h, w = x.shape
+    if out is None:
+        cs = torch.empty((b, c, 2), dtype=torch.float64, device=x.device)
+        buf, off = cs, 0
+    else:
+        buf, off = out
+        cs = buf[:, off:off + c]
+    rc = L.lib().mudiff_gn_stats(x.data_ptr(), c, _pix_ld(x), L.dtype_code(x.dtype), b, h * w,
+                                 buf.data_ptr(), buf.shape[1], off, L.stream_ptr(x.device))
     L.check(rc, 'gn_stats')
-    return stats
+    return cs
 
 
-def gn_apply(srcs, stats, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_NONE,
+def set_chstats(x, cs):
+    setattr(x, _CHSTATS, cs)
+    return x
+
+
+def get_chstats(x):
+    cs = getattr(x, _CHSTATS, None)
+    if cs is None:
+        cs = gn_stats(x)
+        setattr(x, _CHSTATS, cs)
+    return cs
+
+
+def gn_apply(srcs, chstats, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_NONE,
              out_dtype=None, out=None):
     x0 = srcs[0]
     x1 = srcs[1] if len(srcs) > 1 else None
+    s0 = chstats[0]
+    s1 = chstats[1] if len(srcs) > 1 else None
     b, c0, h, w = x0.shape
     c = c0 + (x1.shape[1] if x1 is not None else 0)
     out_dtype = out_dtype or x0.dtype
     if out is None:
         out = empty_nhwc(b, c, h, w, out_dtype, x0.device)
-    rc = L.lib().mudiff_gn_apply(x0.data_ptr(), c0, _pix_ld(x0),
+    rc = L.lib().mudiff_gn_apply(x0.data_ptr(), c0, _pix_ld(x0), s0.data_ptr(), s0.stride(0) // 2,
                                  x1.data_ptr() if x1 is not None else None,
                                  x1.shape[1] if x1 is not None else 0, _pix_ld(x1) if x1 is not None else 0,
-                                 L.dtype_code(x0.dtype), stats.data_ptr(),
+                                 s1.data_ptr() if s1 is not None else None,
+                                 s1.stride(0) // 2 if s1 is not None else 0,
+                                 L.dtype_code(x0.dtype),
                                  gamma.data_ptr() if gamma is not None else None,
                                  beta.data_ptr() if beta is not None else None, gb_bstride,
                                  out.data_ptr(), _pix_ld(out), L.dtype_code(out.dtype), b, h * w, groups,
@@ -161,8 +184,8 @@ def gn_apply(srcs, stats, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6,
 
 
 def group_norm(srcs, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_NONE, out_dtype=None):
-    srcs = [as_nhwc(s) for s in srcs]
-    return gn_apply(srcs, gn_stats(srcs, groups), groups, gamma, beta, gb_bstride, eps, act, out_dtype)
+    srcs = [s if is_nhwc_view(s) else as_nhwc(s) for s in srcs]
+    return gn_apply(srcs, [get_chstats(s) for s in srcs], groups, gamma, beta, gb_bstride, eps, act, out_dtype)
 
 
 # ---------------------------------------------------------------------------------
@@ -187,7 +210,7 @@ def tc_eligible(segs, n, stride, dtype) -> bool:
 
 def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta=0.0, act=L.ACT_NONE,
          out=None, out_coff=0, out_dtype=None, stride=1, pad=1, w_bstride=0, w_ld=0, a_batched=True,
-         batch=None, flags=0, force=None):
+         batch=None, flags=0, force=None, want_stats=False, stats_out=None):
     """Implicit-GEMM convolution.  segs = [(tensor NCHW-logical/channels-last, taps)], wt packed K-major.
     Chooses the tcgen05 kernel when eligible (bf16, Cin % 64 == 0, N % 32 == 0, stride 1), otherwise the
     CUDA-core kernel.  `force` in {None,'tc','simt'}."""
@@ -201,6 +224,7 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
         k = 3 if any(t == 9 for _, t in segs) else 1
         ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
     out_dtype = out_dtype or x0.dtype
+    fresh = out is None
     if out is None:
         out = empty_nhwc(b, n, ho, wo, out_dtype, dev)
     d = L.ConvDesc()
@@ -243,6 +267,14 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
     elif force == 'simt':
         use_tc = False
     st = L.stream_ptr(dev)
+    partial = None
+    tpi = 0
+    if want_stats and use_tc and n <= 256:
+        q = (C.c_int32 * 10)()
+        L.check(L.lib().mudiff_conv_tc_query(C.byref(d), q), 'conv_tc_query')
+        tpi = q[2]
+        partial = torch.empty((b * tpi, n, 2), dtype=torch.float32, device=dev)
+        d.stats = partial.data_ptr()
     prof = None
     if _PROFILER is not None:
         ktot = sum(t.shape[1] * taps for t, taps in segs)
@@ -257,6 +289,21 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
         L.check(L.lib().mudiff_conv_simt(C.byref(d), L.dtype_code(x0.dtype), st), 'conv_simt')
     if prof is not None:
         prof.__exit__(None, None, None)
+    if want_stats:
+        region = out if (fresh or (out_coff == 0 and out.shape[1] == n)) else out[:, out_coff:out_coff + n]
+        if partial is not None:
+            if stats_out is None:
+                cs = torch.empty((b, n, 2), dtype=torch.float64, device=dev)
+                buf, off = cs, 0
+            else:
+                buf, off = stats_out
+                cs = buf[:, off:off + n]
+            L.check(L.lib().mudiff_stats_finalize(partial.data_ptr(), tpi, n, buf.data_ptr(), buf.shape[1], off, b, st),
+                    'stats_finalize')
+        else:
+            cs = gn_stats(region, out=stats_out)
+        if region is out:
+            set_chstats(out, cs)
     return out
 
 

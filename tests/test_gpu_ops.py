@@ -172,8 +172,19 @@ def test_conv_simt_stride2_valid(M):
 
 
 TC_CASES = {
+    # flags: 2 = no halo staging, 8 = no stationary weights, 16 = one pixel tile per unit
     'gemm_1x1':       dict(B=2, H=32, W=32, C=[64], taps=[1], N=64, flags=0),
     'conv3_n64':      dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=2),
+    'conv3_n64_halo_stationary': dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=0),
+    'conv3_n64_halo_stream':     dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=8),
+    'conv3_n64_halo_mt1':        dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=8 | 16),
+    'conv3_n128_halo':           dict(B=3, H=40, W=24, C=[128], taps=[9], N=128, flags=0),
+    'conv3_n256_halo':           dict(B=1, H=32, W=32, C=[256], taps=[9], N=256, flags=0),
+    'conv3_c320_n64':            dict(B=1, H=48, W=40, C=[256, 64], taps=[9, 9], N=64, flags=0),
+    'odd_tiles_halo':            dict(B=3, H=24, W=8, C=[64], taps=[9], N=64, flags=0),
+    'fused_shortcut_halo':       dict(B=2, H=32, W=32, C=[64, 128, 64], taps=[9, 1, 1], N=64, flags=0, epi=True),
+    'fused_shortcut_n128':       dict(B=2, H=16, W=16, C=[128, 64], taps=[9, 1], N=128, flags=0, epi=True),
+    'n384_sigmoid_halo':         dict(B=1, H=32, W=32, C=[192], taps=[9], N=384, flags=0, act=2),
     'conv3_n256':     dict(B=1, H=32, W=32, C=[128], taps=[9], N=256, flags=2),
     'conv3_ragged':   dict(B=3, H=24, W=20, C=[64], taps=[9], N=128, flags=2),
     'conv3_small':    dict(B=2, H=8, W=8, C=[256], taps=[9], N=256, flags=2),
@@ -211,9 +222,16 @@ def test_conv_tc_vs_fp32_reference(M, name):
         ref = torch.sigmoid(ref)
         kw['act'] = 2
     wt = torch.cat(ws, dim=1).contiguous()
-    out = ops.conv(segs, wt, N, out_dtype=torch.float32, flags=c['flags'], force='tc', **kw)
+    out = ops.conv(segs, wt, N, out_dtype=torch.float32, flags=c['flags'], force='tc', want_stats=N <= 256, **kw)
     scale = max(ref.abs().max().item(), 1.0)
-    assert (out.cpu() - ref).abs().max().item() <= 2e-3 * scale
+    tol = 5e-3 if c.get('act') == 2 else 2e-3          # sigmoid epilogue uses tanh.approx
+    assert (out.cpu() - ref).abs().max().item() <= tol * scale
+    if N <= 256:
+        # fused epilogue statistics == per-channel (sum, sumsq) of the tensor that was written
+        cs = ops.get_chstats(out).cpu()
+        o64 = out.double().cpu()
+        np.testing.assert_allclose(cs[..., 0].numpy(), o64.sum(dim=(2, 3)).numpy(), rtol=1e-5, atol=1e-3)
+        np.testing.assert_allclose(cs[..., 1].numpy(), (o64 ** 2).sum(dim=(2, 3)).numpy(), rtol=1e-5, atol=1e-3)
 
 
 def test_conv_tc_batched_weights_qk(M):

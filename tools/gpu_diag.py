@@ -12,21 +12,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 CASES = {
-    # name: (B, H, W, [Cin per seg], [taps per seg], N, flags, extras)
-    'gemm_1x1_n64':      dict(B=2, H=32, W=32, C=[64], taps=[1], N=64, flags=0),
-    'gemm_1x1_k256_n256': dict(B=1, H=16, W=64, C=[256], taps=[1], N=256, flags=0),
-    'conv3_pertap_n64':  dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=2),
-    'conv3_pertap_n256': dict(B=1, H=32, W=32, C=[128], taps=[9], N=256, flags=2),
-    'conv3_halo_n64':    dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=1),
-    'conv3_halo_bo_n64': dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=1 | 4),
-    'conv3_halo_c192':   dict(B=1, H=48, W=40, C=[192], taps=[9], N=64, flags=1),
-    'conv3_ragged':      dict(B=3, H=24, W=20, C=[64], taps=[9], N=128, flags=2),
-    'fused_shortcut':    dict(B=2, H=32, W=32, C=[64, 128, 64], taps=[9, 1, 1], N=64, flags=2, epi=True),
-    'fused_shortcut_halo': dict(B=2, H=32, W=32, C=[64, 128, 64], taps=[9, 1, 1], N=64, flags=1, epi=True),
-    'n384_sigmoid':      dict(B=1, H=32, W=32, C=[192], taps=[9], N=384, flags=2, act=2),
-    'gemm_mode_h1':      dict(B=2, H=1, W=256, C=[128], taps=[1], N=256, flags=0),
-    'many_tiles':        dict(B=8, H=64, W=64, C=[64], taps=[9], N=64, flags=2),
-    'many_tiles_halo':   dict(B=8, H=64, W=64, C=[64], taps=[9], N=64, flags=1),
+    # flags: 2 = no halo staging, 8 = no stationary weights, 16 = one pixel tile per unit
+    'gemm_1x1_n64':        dict(B=2, H=32, W=32, C=[64], taps=[1], N=64, flags=0),
+    'conv3_pertap_n64':    dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=2),
+    'conv3_halo_stat_n64': dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=0),
+    'conv3_halo_strm_n64': dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=8),
+    'conv3_halo_mt1_n64':  dict(B=2, H=32, W=32, C=[64], taps=[9], N=64, flags=8 | 16),
+    'conv3_halo_n128':     dict(B=3, H=40, W=24, C=[128], taps=[9], N=128, flags=0),
+    'conv3_halo_n256':     dict(B=1, H=32, W=32, C=[256], taps=[9], N=256, flags=0),
+    'conv3_c320_n64':      dict(B=1, H=48, W=40, C=[256, 64], taps=[9, 9], N=64, flags=0),
+    'fused_shortcut':      dict(B=2, H=32, W=32, C=[64, 128, 64], taps=[9, 1, 1], N=64, flags=0, epi=True),
+    'n384_sigmoid':        dict(B=1, H=32, W=32, C=[192], taps=[9], N=384, flags=0, act=2),
+    'gemm_mode_h1':        dict(B=2, H=1, W=256, C=[128], taps=[1], N=256, flags=0),
+    'many_tiles':          dict(B=8, H=64, W=64, C=[64], taps=[9], N=64, flags=0),
+    'many_tiles_n128':     dict(B=8, H=64, W=64, C=[128], taps=[9], N=128, flags=0),
 }
 
 
@@ -69,7 +68,7 @@ def run_case(name):
     out16 = ops.conv(segs, wt, N, out_dtype=torch.bfloat16, flags=c['flags'], force='tc', **kw2)
     torch.cuda.synchronize()
     err16 = (out16.float() - ref).abs().max().item()
-    ok = err < 2e-3 * max(scale, 1.0)
+    ok = err < 5e-3 * max(scale, 1.0)
     print(f"CASE {name}: max|err| f32-out {err:.3e}  bf16-out {err16:.3e}  (|ref|max {scale:.3f})  {'OK' if ok else 'MISMATCH'}")
     if not ok:
         d = (out - ref).abs()
