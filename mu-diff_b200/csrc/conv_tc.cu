@@ -40,6 +40,7 @@ struct TcParams {
   uint32_t idesc;
   int acc_stride, acc_stages, tmem_cols;
   int base_off_variant;
+  int round_robin;                            // debug: interleaved instead of contiguous unit assignment
   // epilogue
   const float* bias; const float* rowbias; int rowbias_ld;
   const void* residual; int res_ld;
@@ -211,14 +212,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   // contiguous, balanced range of units for this CTA
-  const long long u_begin = (p.total_units * (long long)blockIdx.x) / gridDim.x;
-  const long long u_end = (p.total_units * (long long)(blockIdx.x + 1)) / gridDim.x;
+  const long long u_begin = p.round_robin ? (long long)blockIdx.x : (p.total_units * (long long)blockIdx.x) / gridDim.x;
+  const long long u_end = p.round_robin ? p.total_units : (p.total_units * (long long)(blockIdx.x + 1)) / gridDim.x;
+  const long long u_step = p.round_robin ? (long long)gridDim.x : 1;
 
   if (warp == 0) {
     // =========================== A producer ===========================
     if (lane == 0) {
       uint32_t a_item = 0;
-      for (long long u = u_begin; u < u_end; ++u) {
+      for (long long u = u_begin; u < u_end; u += u_step) {
         const Unit un = decode_unit(p, u);
         const int ab = p.a_batched ? un.b : 0;
         for_each_group(p, [&](int s, int cb, int tap, int nb) {
@@ -254,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           tma_load_3d(smem + p.off_b + (size_t)i * p.b_sub_bytes, &mapW, w_full, i * 64, 0, 0);
       } else {
         uint32_t b_item = 0;
-        for (long long u = u_begin; u < u_end; ++u) {
+        for (long long u = u_begin; u < u_end; u += u_step) {
           const Unit un = decode_unit(p, u);
           const int wb = p.w_batched ? un.b : 0;
           for_each_group(p, [&](int s, int cb, int tap, int nb) {
@@ -279,7 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t smem_base = smem_u32(smem);
       if (p.stationary) { mbar_wait(w_full, 0); tc_fence_after(); }
-      for (long long u = u_begin; u < u_end; ++u) {
+      for (long long u = u_begin; u < u_end; u += u_step) {
         const Unit un = decode_unit(p, u);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -331,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int ty_in = row / p.tile_w, tx_in = row - ty_in * p.tile_w;
     float* sstat = (float*)(smem + p.off_stats);   // [4 warps][n_tile][2]
     int acc = 0; uint32_t acc_phase = 0;
-    for (long long u = u_begin; u < u_end; ++u) {
+    for (long long u = u_begin; u < u_end; u += u_step) {
       const Unit un = decode_unit(p, u);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -612,6 +614,7 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   // UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, N = n_tile, M = 128
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((128u >> 4) << 24);
   p.base_off_variant = (d->flags & 4) ? 1 : 0;
+  p.round_robin = (d->flags & 32) ? 1 : 0;
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
   p.residual = d->residual; p.res_ld = d->res_ld; p.alpha = d->alpha; p.beta = d->beta; p.act = d->act;
   p.out = d->out; p.out_ld = d->out_ld; p.out_coff = d->out_coff;

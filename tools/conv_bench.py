@@ -1,0 +1,53 @@
+"""Micro-benchmark of conv_tc variants (ablation flags) on representative generator shapes."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import mudiff_b200 as M
+from mudiff_b200 import ops
+
+B = int(os.environ.get('CB_BATCH', '16'))
+SHAPES = [  # (H, Cin list, taps, N)
+    (256, [64], [9], 64),
+    (256, [256], [9], 64),
+    (256, [64, 128, 64], [9, 1, 1], 64),
+    (128, [128], [9], 128),
+    (128, [256, 128], [9, 9], 128),
+    (64, [256], [9], 256),
+    (64, [512], [9], 256),
+    (256, [192], [9], 384),
+]
+VARIANTS = [('default', 0), ('rr', 32), ('nostat', 8), ('mt1', 16), ('nostat+mt1', 24), ('pertap', 2), ('pertap+mt1', 18),
+            ('rr+nostat+mt1', 56), ('rr+pertap+mt1', 50)]
+
+
+def bench(fn, iters=5):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+for H, cins, taps, N in SHAPES:
+    segs, ws = [], []
+    for ci, tp in zip(cins, taps):
+        x = torch.randn(B, ci, H, H, device='cuda').to(torch.bfloat16)
+        k = 3 if tp == 9 else 1
+        w = (torch.randn(N, ci, k, k, device='cuda') / (ci * tp) ** 0.5).to(torch.bfloat16)
+        segs.append((ops.as_nhwc(x), tp)); ws.append(ops.pack_conv_weight(w, (ci,), torch.bfloat16))
+    wt = torch.cat(ws, 1).contiguous()
+    ktot = wt.shape[1]
+    flops = 2.0 * B * H * H * N * ktot
+    out = ops.empty_nhwc(B, N, H, H, torch.bfloat16, 'cuda')
+    line = f"H={H:3d} Cin={cins} N={N:3d} K={ktot:5d}: "
+    for name, fl in VARIANTS:
+        for st in ((0, 1) if name in ('default', 'rr') and N <= 256 else (0,)):
+            try:
+                ms = bench(lambda: ops.conv(segs, wt, N, out=out, flags=fl, force='tc', want_stats=bool(st)))
+                line += f"{name}{'+stats' if st else ''}={flops / ms / 1e9:6.0f}  "
+            except RuntimeError as e:
+                line += f"{name}=ERR  "
+    print(line, flush=True)
