@@ -113,6 +113,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled UMMA shared-memory descriptor.
@@ -276,53 +281,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
   } else if (warp == 2) {
     // =========================== MMA issuer =============================
-    if (lane == 0) {
-      uint32_t a_item = 0, b_item = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      const uint32_t smem_base = smem_u32(smem);
-      if (p.stationary) { mbar_wait(w_full, 0); tc_fence_after(); }
-      for (long long u = u_begin; u < u_end; u += u_step) {
-        const Unit un = decode_unit(p, u);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        bool first = true;
-        for_each_group(p, [&](int s, int cb, int tap, int nb) {
-          const bool halo = nb == 9;
-          const uint32_t sbo_a = halo ? (uint32_t)(p.tile_w + 2) * 128u : 1024u;
-          for (int j = 0; j < nb; ++j) {
-            uint32_t sb, bslot = 0;
-            if (p.stationary) {
-              const int ksub = (p.seg_koff[s] + (halo ? j : tap) * p.seg_c[s]) / 64 + cb;
-              sb = smem_base + p.off_b + (uint32_t)ksub * p.b_sub_bytes;
-            } else {
-              bslot = b_item % (uint32_t)p.b_slots;
-              mbar_wait(&b_full[bslot], (b_item / (uint32_t)p.b_slots) & 1u);
-              sb = smem_base + p.off_b + bslot * p.b_sub_bytes;
-            }
-            tc_fence_after();
-            const uint32_t a_off = halo ? (uint32_t)((j / 3) * (p.tile_w + 2) + (j % 3)) * 128u : 0u;
-            for (int m = 0; m < un.count; ++m) {
-              const uint32_t it = a_item + (uint32_t)m;
-              const uint32_t aslot = it % (uint32_t)p.a_slots;
-              if (j == 0) { mbar_wait(&a_full[aslot], (it / (uint32_t)p.a_slots) & 1u); tc_fence_after(); }
-              const uint32_t sa = smem_base + aslot * p.a_slot_bytes;
-              const uint32_t d_tmem = tmem_base + (uint32_t)((acc * p.MT + m) * p.acc_stride);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = umma_desc(sa + a_off + k * 32u, sbo_a, p.base_off_variant);
-                const uint64_t bd = umma_desc(sb + k * 32u, 1024u, 0);
-                tc_mma_f16(d_tmem, ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
-              }
-              if (j == nb - 1) tc_commit(&a_empty[aslot]);      // this A tile is done after its last tap
-            }
-            if (!p.stationary) { tc_commit(&b_empty[bslot]); ++b_item; }
-            first = false;
+    // The WHOLE warp walks the loop (warp-uniform control flow and operands, so descriptors live in
+    // uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.  The per-MMA work is
+    // two 64-bit adds: the single-thread issue rate bounds every N <= 128 shape.
+    const bool leader = elect_one();
+    uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t hi_b = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t hi_a_halo = (((uint32_t)(p.tile_w + 2) * 128u) >> 4) | (1u << 14) | (2u << 29);
+    if (p.stationary) { mbar_wait(w_full, 0); tc_fence_after(); }
+    for (long long u = u_begin; u < u_end; u += u_step) {
+      const Unit un = decode_unit(p, u);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      uint32_t accum = 0;                                  // 0 only for the first MMA of each accumulator
+      for_each_group(p, [&](int s, int cb, int tap, int nb) {
+        const bool halo = nb == 9;
+        const uint32_t hi_a = halo ? hi_a_halo : hi_b;
+        for (int j = 0; j < nb; ++j) {
+          uint32_t sb;
+          if (p.stationary) {
+            const int ksub = (p.seg_koff[s] + (halo ? j : tap) * p.seg_c[s]) / 64 + cb;
+            sb = smem_base + p.off_b + (uint32_t)ksub * p.b_sub_bytes;
+          } else {
+            mbar_wait(&b_full[b_slot], b_phase);
+            sb = smem_base + p.off_b + b_slot * p.b_sub_bytes;
           }
-          a_item += (uint32_t)un.count;
-        });
-        tc_commit(&tfull_bar[acc]);                // accumulators complete -> epilogue
-        if (p.acc_stages == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
-      }
+          tc_fence_after();
+          const uint64_t bd0 = ((uint64_t)hi_b << 32) | (uint64_t)(((sb & 0x3FFFFu) >> 4) | (1u << 16));
+          const uint32_t a_off = halo ? (uint32_t)((j / 3) * (p.tile_w + 2) + (j % 3)) * 128u : 0u;
+          uint32_t sl = a_slot, ph = a_phase;
+          for (int m = 0; m < un.count; ++m) {
+            if (j == 0) { mbar_wait(&a_full[sl], ph); tc_fence_after(); }
+            const uint32_t sa = smem_base + sl * p.a_slot_bytes + a_off;
+            const uint64_t ad0 = ((uint64_t)hi_a << 32) | (uint64_t)(((sa & 0x3FFFFu) >> 4) | (1u << 16));
+            const uint32_t d_tmem = tmem_base + (uint32_t)((acc * p.MT + m) * p.acc_stride);
+            if (leader) {
+              tc_mma_f16(d_tmem, ad0, bd0, p.idesc, accum);
+              tc_mma_f16(d_tmem, ad0 + 2, bd0 + 2, p.idesc, 1u);
+              tc_mma_f16(d_tmem, ad0 + 4, bd0 + 4, p.idesc, 1u);
+              tc_mma_f16(d_tmem, ad0 + 6, bd0 + 6, p.idesc, 1u);
+              if (j == nb - 1) tc_commit(&a_empty[sl]);        // this A tile is done after its last tap
+            }
+            if (++sl == (uint32_t)p.a_slots) { sl = 0; ph ^= 1u; }
+          }
+          if (!p.stationary) {
+            if (leader) tc_commit(&b_empty[b_slot]);
+            if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_phase ^= 1u; }
+          }
+          accum = 1u;
+        }
+        a_slot += (uint32_t)un.count;
+        if (a_slot >= (uint32_t)p.a_slots) { a_slot -= (uint32_t)p.a_slots; a_phase ^= 1u; }
+      });
+      if (leader) tc_commit(&tfull_bar[acc]);                // accumulators complete -> epilogue
+      if (p.acc_stages == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
+      __syncwarp();
     }
   } else {
     // =========================== epilogue ===============================
