@@ -41,6 +41,7 @@ struct TcParams {
   int acc_stride, acc_stages, tmem_cols;
   int base_off_variant;
   int round_robin;                            // debug: interleaved instead of contiguous unit assignment
+  int dbg_dry, dbg_noepi;                     // debug: no operand traffic / no epilogue work (timing only)
   // epilogue
   const float* bias; const float* rowbias; int rowbias_ld;
   const void* residual; int res_ld;
@@ -223,7 +224,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
   if (warp == 0) {
     // =========================== A producer ===========================
-    if (lane == 0) {
+    if (lane == 0 && !p.dbg_dry) {
       uint32_t a_item = 0;
       for (long long u = u_begin; u < u_end; u += u_step) {
         const Unit un = decode_unit(p, u);
@@ -254,7 +255,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
   } else if (warp == 1) {
     // =========================== B producer ===========================
-    if (lane == 0) {
+    if (lane == 0 && !p.dbg_dry) {
       if (p.stationary) {
         mbar_expect_tx(w_full, (uint32_t)p.b_total_subs * p.b_sub_bytes);
         for (int i = 0; i < p.b_total_subs; ++i)
@@ -281,56 +282,79 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
   } else if (warp == 2) {
     // =========================== MMA issuer =============================
-    // The WHOLE warp walks the loop (warp-uniform control flow and operands, so descriptors live in
-    // uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.  The per-MMA work is
-    // two 64-bit adds: the single-thread issue rate bounds every N <= 128 shape.
+    // The issue rate of this single warp bounds every N <= 192 shape (UMMA 128xNx16 needs < 100 clk of
+    // tensor time), so the loop is kept as lean as possible: lane 0 polls the mbarriers, the warp
+    // re-converges, descriptor low words are precomputed per group and advanced with immediates.
     const bool leader = elect_one();
     uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t hi_b = (1024u >> 4) | (1u << 14) | (2u << 29);
-    const uint32_t hi_a_halo = (((uint32_t)(p.tile_w + 2) * 128u) >> 4) | (1u << 14) | (2u << 29);
-    if (p.stationary) { mbar_wait(w_full, 0); tc_fence_after(); }
+    const uint32_t hi_a_halo = ((10u * 128u) >> 4) | (1u << 14) | (2u << 29);     // halo tiles are 8 wide: pitch 10 px
+    const uint32_t b_lo_base = (((smem_base + p.off_b) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t b_step = p.b_sub_bytes >> 4;
+    const uint32_t a_lo_base = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t a_step = p.a_slot_bytes >> 4;
+    const bool dry = p.dbg_dry != 0;
+    if (p.stationary && !dry) { if (leader) mbar_wait(w_full, 0); __syncwarp(); tc_fence_after(); }
     for (long long u = u_begin; u < u_end; u += u_step) {
       const Unit un = decode_unit(p, u);
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      if (leader) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      __syncwarp();
       tc_fence_after();
       uint32_t accum = 0;                                  // 0 only for the first MMA of each accumulator
+      const uint32_t d0 = tmem_base + (uint32_t)((acc * p.MT) * p.acc_stride);
+      const uint32_t d1 = d0 + (uint32_t)p.acc_stride;
+      const bool two = un.count > 1;
       for_each_group(p, [&](int s, int cb, int tap, int nb) {
-        const bool halo = nb == 9;
-        const uint32_t hi_a = halo ? hi_a_halo : hi_b;
-        for (int j = 0; j < nb; ++j) {
-          uint32_t sb;
-          if (p.stationary) {
-            const int ksub = (p.seg_koff[s] + (halo ? j : tap) * p.seg_c[s]) / 64 + cb;
-            sb = smem_base + p.off_b + (uint32_t)ksub * p.b_sub_bytes;
-          } else {
-            mbar_wait(&b_full[b_slot], b_phase);
-            sb = smem_base + p.off_b + b_slot * p.b_sub_bytes;
-          }
-          tc_fence_after();
-          const uint64_t bd0 = ((uint64_t)hi_b << 32) | (uint64_t)(((sb & 0x3FFFFu) >> 4) | (1u << 16));
-          const uint32_t a_off = halo ? (uint32_t)((j / 3) * (p.tile_w + 2) + (j % 3)) * 128u : 0u;
-          uint32_t sl = a_slot, ph = a_phase;
-          for (int m = 0; m < un.count; ++m) {
-            if (j == 0) { mbar_wait(&a_full[sl], ph); tc_fence_after(); }
-            const uint32_t sa = smem_base + sl * p.a_slot_bytes + a_off;
-            const uint64_t ad0 = ((uint64_t)hi_a << 32) | (uint64_t)(((sa & 0x3FFFFu) >> 4) | (1u << 16));
-            const uint32_t d_tmem = tmem_base + (uint32_t)((acc * p.MT + m) * p.acc_stride);
-            if (leader) {
-              tc_mma_f16(d_tmem, ad0, bd0, p.idesc, accum);
-              tc_mma_f16(d_tmem, ad0 + 2, bd0 + 2, p.idesc, 1u);
-              tc_mma_f16(d_tmem, ad0 + 4, bd0 + 4, p.idesc, 1u);
-              tc_mma_f16(d_tmem, ad0 + 6, bd0 + 6, p.idesc, 1u);
-              if (j == nb - 1) tc_commit(&a_empty[sl]);        // this A tile is done after its last tap
+        // A tiles of this group (one or two pixel tiles)
+        const uint32_t sl0 = a_slot;
+        uint32_t sl1 = a_slot + 1, ph1 = a_phase;
+        if (sl1 == (uint32_t)p.a_slots) { sl1 = 0; ph1 ^= 1u; }
+        if (leader && !dry) { mbar_wait(&a_full[sl0], a_phase); if (two) mbar_wait(&a_full[sl1], ph1); }
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t alo0 = a_lo_base + sl0 * a_step;
+        const uint32_t alo1 = a_lo_base + sl1 * a_step;
+        const uint32_t hi_a = nb == 9 ? hi_a_halo : hi_b;
+        const int kbase = (p.seg_koff[s] + (nb == 9 ? 0 : tap) * p.seg_c[s]) / 64 + cb;   // stationary sub-tile index of tap 0
+        const int kstep = p.seg_c[s] / 64;                                                   // ... and its stride per tap
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          if (j < nb) {
+            uint32_t blo;
+            if (p.stationary) {
+              blo = b_lo_base + (uint32_t)(kbase + j * kstep) * b_step;
+            } else {
+              if (leader && !dry) mbar_wait(&b_full[b_slot], b_phase);
+              __syncwarp();
+              tc_fence_after();
+              blo = b_lo_base + b_slot * b_step;
             }
-            if (++sl == (uint32_t)p.a_slots) { sl = 0; ph ^= 1u; }
+            const uint32_t toff = (uint32_t)((j / 3) * 10 + (j % 3)) * 8u;     // tap offset in 16-byte units (halo only; j == 0 otherwise)
+            if (leader) {
+              const uint64_t bd = ((uint64_t)hi_b << 32) | blo;
+              const uint64_t ad = ((uint64_t)hi_a << 32) | (alo0 + toff);
+              tc_mma_f16(d0, ad, bd, p.idesc, accum);
+              tc_mma_f16(d0, ad + 2, bd + 2, p.idesc, 1u);
+              tc_mma_f16(d0, ad + 4, bd + 4, p.idesc, 1u);
+              tc_mma_f16(d0, ad + 6, bd + 6, p.idesc, 1u);
+              if (two) {
+                const uint64_t ae = ((uint64_t)hi_a << 32) | (alo1 + toff);
+                tc_mma_f16(d1, ae, bd, p.idesc, accum);
+                tc_mma_f16(d1, ae + 2, bd + 2, p.idesc, 1u);
+                tc_mma_f16(d1, ae + 4, bd + 4, p.idesc, 1u);
+                tc_mma_f16(d1, ae + 6, bd + 6, p.idesc, 1u);
+              }
+              if (!p.stationary) tc_commit(&b_empty[b_slot]);
+            }
+            if (!p.stationary) { if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_phase ^= 1u; } }
+            accum = 1u;
           }
-          if (!p.stationary) {
-            if (leader) tc_commit(&b_empty[b_slot]);
-            if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_phase ^= 1u; }
-          }
-          accum = 1u;
+        }
+        if (leader) {                                         // both A tiles are free once the last tap retires
+          tc_commit(&a_empty[sl0]);
+          if (two) tc_commit(&a_empty[sl1]);
         }
         a_slot += (uint32_t)un.count;
         if (a_slot >= (uint32_t)p.a_slots) { a_slot -= (uint32_t)p.a_slots; a_phase ^= 1u; }
@@ -352,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const Unit un = decode_unit(p, u);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      for (int m = 0; m < un.count; ++m) {
+      for (int m = 0; m < (p.dbg_noepi ? 0 : un.count); ++m) {
         const int r = un.r0 + m;
         const int tyt = r / p.tiles_x;
         const int y = tyt * p.tile_h + ty_in, x = (r - tyt * p.tiles_x) * p.tile_w + tx_in;
@@ -630,6 +654,8 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((128u >> 4) << 24);
   p.base_off_variant = (d->flags & 4) ? 1 : 0;
   p.round_robin = (d->flags & 32) ? 1 : 0;
+  p.dbg_dry = (d->flags & 64) ? 1 : 0;
+  p.dbg_noepi = (d->flags & 128) ? 1 : 0;
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
   p.residual = d->residual; p.res_ld = d->res_ld; p.alpha = d->alpha; p.beta = d->beta; p.act = d->act;
   p.out = d->out; p.out_ld = d->out_ld; p.out_coff = d->out_coff;

@@ -17,8 +17,7 @@ SHAPES = [  # (H, Cin list, taps, N)
     (64, [512], [9], 256),
     (256, [192], [9], 384),
 ]
-VARIANTS = [('default', 0), ('rr', 32), ('nostat', 8), ('mt1', 16), ('nostat+mt1', 24), ('pertap', 2), ('pertap+mt1', 18),
-            ('rr+nostat+mt1', 56), ('rr+pertap+mt1', 50)]
+VARIANTS = [('default', 0), ('dry', 64), ('noepi', 128), ('dry+noepi', 192), ('mt1', 16), ('mt1+dry+noepi', 16 + 192), ('pertap', 2)]
 
 
 def bench(fn, iters=5):
@@ -44,7 +43,7 @@ for H, cins, taps, N in SHAPES:
     out = ops.empty_nhwc(B, N, H, H, torch.bfloat16, 'cuda')
     line = f"H={H:3d} Cin={cins} N={N:3d} K={ktot:5d}: "
     for name, fl in VARIANTS:
-        for st in ((0, 1) if name in ('default', 'rr') and N <= 256 else (0,)):
+        for st in ((0, 1) if name in ('default', 'dry') and N <= 256 else (0,)):
             try:
                 ms = bench(lambda: ops.conv(segs, wt, N, out=out, flags=fl, force='tc', want_stats=bool(st)))
                 line += f"{name}{'+stats' if st else ''}={flops / ms / 1e9:6.0f}  "
