@@ -23,7 +23,7 @@
 namespace {
 
 constexpr int kMaxSlots = 16;
-constexpr int kThreads = 224;
+constexpr int kThreads = 352;               // 3 producer/MMA warps + 8 epilogue warps
 constexpr uint32_t kSmemMax = 232448;       // 227 KB opt-in limit per CTA
 
 struct TcParams {
@@ -201,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -366,14 +366,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else {
     // =========================== epilogue ===============================
     const int q = warp & 3;                        // TMEM lane quadrant this warp may read
-    const int ew = warp - 3;                       // epilogue warp index 0..3
-    const int et = ew * 32 + lane;                 // epilogue thread index 0..127
+    const int half = (warp - 3) >> 2;              // two warps share a lane quadrant: even / odd 32-column chunks
+    const int et = (warp - 3) * 32 + lane;         // epilogue thread index 0..255
     const int row = q * 32 + lane;                 // accumulator row == pixel within the tile
     const int ty_in = row / p.tile_w, tx_in = row - ty_in * p.tile_w;
-    float* sstat = (float*)(smem + p.off_stats);   // [4 warps][n_tile][2]
+    float* sstat = (float*)(smem + p.off_stats);   // [4 quadrants][n_tile][2]
+    float* sbias = sstat + 8 * p.n_tile;           // [n_tile] bias + row-bias of the current image
+    int bias_b = -1, bias_n0 = -1;
     int acc = 0; uint32_t acc_phase = 0;
     for (long long u = u_begin; u < u_end; u += u_step) {
       const Unit un = decode_unit(p, u);
+      if ((p.bias || p.rowbias) && (un.b != bias_b || un.n0 != bias_n0)) {
+        // stage bias[n] + rowbias[b][n] once per (image, N tile); all 256 epilogue threads take part
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        for (int col = et; col < p.n_tile; col += 256) {
+          float bv = p.bias ? __ldg(p.bias + un.n0 + col) : 0.f;
+          if (p.rowbias) bv += __ldg(p.rowbias + (int64_t)un.b * p.rowbias_ld + un.n0 + col);
+          sbias[col] = bv;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        bias_b = un.b; bias_n0 = un.n0;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       for (int m = 0; m < (p.dbg_noepi ? 0 : un.count); ++m) {
@@ -383,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const bool valid = (y < p.H) && (x < p.W);
         const int64_t pix = ((int64_t)un.b * p.H + y) * p.W + x;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.MT + m) * p.acc_stride);
-        for (int c = 0; c < p.n_tile; c += 32) {
+        for (int c = half * 32; c < p.n_tile; c += 64) {
           uint32_t v[32];
           tmem_ld32(taddr0 + (uint32_t)c, v);
           tmem_ld_wait();
@@ -392,14 +405,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (valid) {
-            if (p.bias) {
+            if (p.bias || p.rowbias) {
+              const float4* sb4 = reinterpret_cast<const float4*>(sbias + c);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + n + j);
-            }
-            if (p.rowbias) {
-              const float* rb = p.rowbias + (int64_t)un.b * p.rowbias_ld + n;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += __ldg(rb + j);
+              for (int j = 0; j < 8; ++j) {
+                const float4 bv = sb4[j];
+                f[4 * j + 0] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
+              }
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
@@ -465,14 +477,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
             const float cs = warp_transpose_reduce(f, lane);
             const float cq = warp_transpose_reduce(sq, lane);
-            sstat[((ew * p.n_tile) + c + lane) * 2 + 0] = cs;
-            sstat[((ew * p.n_tile) + c + lane) * 2 + 1] = cq;
+            sstat[((q * p.n_tile) + c + lane) * 2 + 0] = cs;
+            sstat[((q * p.n_tile) + c + lane) * 2 + 1] = cq;
           }
         }
         if (p.stats_partial) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           float* dst = p.stats_partial + (((int64_t)un.b * p.tpi + r) * p.n_total + un.n0) * 2;
-          for (int col = et; col < p.n_tile; col += 128) {
+          for (int col = et; col < p.n_tile; col += 256) {
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
@@ -481,7 +493,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             *reinterpret_cast<float2*>(dst + col * 2) = make_float2(s0, s1);
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
       }
       tc_fence_before();
@@ -617,7 +629,7 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   p.total_units = (long long)d->batch * p.gpi * p.n_tiles;
   // shared memory plan
   const uint32_t bar_bytes = 1024;
-  const uint32_t stats_bytes = d->stats ? (uint32_t)n_tile * 32u : 0u;
+  const uint32_t stats_bytes = (uint32_t)n_tile * 36u;       // [4][n_tile][2] statistics staging + [n_tile] bias staging
   const uint32_t fixed = bar_bytes + ((stats_bytes + 1023u) & ~1023u) + 1024u /*alignment slack*/;
   const uint32_t avail = kSmemMax - fixed;
   const uint32_t b_total = (uint32_t)(ktot / 64) * p.b_sub_bytes;
