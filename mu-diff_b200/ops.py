@@ -16,6 +16,8 @@ SQRT2_INV = 1.0 / math.sqrt(2.0)
 import os as _os
 _ENV_FLAGS = 2 if _os.environ.get('MUDIFF_HALO', '1') == '0' else 0     # debug knob: forbid halo staging
 
+FUSED_STATS_MIN_N = int(_os.environ.get('MUDIFF_FUSED_STATS_MIN_N', '128'))
+
 # Optional per-launch profiler (bench.py): callable(kind, flops, bytes) -> context manager or None.
 _PROFILER = None
 
@@ -269,7 +271,9 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
     st = L.stream_ptr(dev)
     partial = None
     tpi = 0
-    if want_stats and use_tc and n <= 256:
+    # fused epilogue statistics pay off only when the MMA phase of a tile is long enough to hide the
+    # butterfly reduction (N >= 128); N = 64 outputs get a stand-alone statistics pass (HBM-bound, cheaper)
+    if want_stats and use_tc and FUSED_STATS_MIN_N <= n <= 256:
         q = (C.c_int32 * 10)()
         L.check(L.lib().mudiff_conv_tc_query(C.byref(d), q), 'conv_tc_query')
         tpi = q[2]
