@@ -163,6 +163,10 @@ int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream);
 /* Planning only: out[0..9] = tile_h, tile_w, tiles_per_image, n_tile, tiles_per_unit, stationary_weights,
  * a_slots, b_slots, accumulator_stages, halo(seg0).  Callers size `stats` with out[2]. */
 int mudiff_conv_tc_query(const mudiff_conv_desc* d, int32_t* out);
+/* Debug: out[0..7] = (timed_out, block, warp, lane, barrier smem address, parity, grid, 0) of the last mbarrier
+ * wait that hit its 4e9-cycle bound inside mudiff_conv_tc (kept in mapped host memory). */
+int mudiff_debug_last_timeout(int32_t* out);
+int mudiff_debug_selftest(void);   /* 1 if the mapped-host debug channel works */
 /* CUDA-core implicit GEMM (fp32 or bf16 storage, fp32 math): any shape, stride 1/2.
  * This is the fp32-parity path and the path for Cin=1 / Cout=1 / strided convs. */
 int mudiff_conv_simt(const mudiff_conv_desc* d, int dtype, void* stream);

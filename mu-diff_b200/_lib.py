@@ -53,6 +53,8 @@ PROTOTYPES = {
     'mudiff_zero': [_P, _L, _P],
     'mudiff_conv_tc': [C.POINTER(ConvDesc), _P],
     'mudiff_conv_tc_query': [C.POINTER(ConvDesc), C.POINTER(C.c_int32)],
+    'mudiff_debug_last_timeout': [C.POINTER(C.c_int32)],
+    'mudiff_debug_selftest': [],
     'mudiff_conv_simt': [C.POINTER(ConvDesc), _I, _P],
     'mudiff_softmax_rows': [_P, _P, _I, _L, _I, _F, _P],
     'mudiff_linear': [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
@@ -133,7 +135,13 @@ def check(rc: int, what: str):
         raise RuntimeError(f"mu-diff_b200: {what}: invalid argument")
     if rc == EUNSUPPORTED:
         raise RuntimeError(f"mu-diff_b200: {what}: unsupported shape/dtype for this kernel")
-    raise RuntimeError(f"mu-diff_b200: {what}: CUDA error {rc}")
+    info = (C.c_int32 * 8)()
+    try:
+        lib().mudiff_debug_last_timeout(info)
+    except Exception:
+        pass
+    extra = f" [mbarrier wait timed out: block {info[1]} warp {info[2]} lane {info[3]} bar@{info[4]:#x} parity {info[5]} grid {info[6]}]" if info[0] else ""
+    raise RuntimeError(f"mu-diff_b200: {what}: CUDA error {rc}{extra}")
 
 
 def require_cuda(*tensors):

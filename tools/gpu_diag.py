@@ -24,6 +24,24 @@ CASES = {
     'fused_shortcut':      dict(B=2, H=32, W=32, C=[64, 128, 64], taps=[9, 1, 1], N=64, flags=0, epi=True),
     'n384_sigmoid':        dict(B=1, H=32, W=32, C=[192], taps=[9], N=384, flags=0, act=2),
     'gemm_mode_h1':        dict(B=2, H=1, W=256, C=[128], taps=[1], N=256, flags=0),
+    'g_w4096_n256':        dict(B=2, H=1, W=4096, C=[256], taps=[1], N=256, flags=0),
+    'g_w512_n4096':        dict(B=4, H=1, W=512, C=[256], taps=[1], N=4096, flags=0),
+    'g_w4096_n4096_dry':   dict(B=2, H=1, W=4096, C=[256], taps=[1], N=4096, flags=64),
+    'g_w4096_n4096_noepi': dict(B=2, H=1, W=4096, C=[256], taps=[1], N=4096, flags=128),
+    'g_w4096_n4096_rr':    dict(B=2, H=1, W=4096, C=[256], taps=[1], N=4096, flags=32),
+    'c_mt1_multi':         dict(B=4, H=128, W=128, C=[128], taps=[9], N=128, flags=16),
+    'c_n256_multi':        dict(B=8, H=64, W=64, C=[128], taps=[9], N=256, flags=0),
+    'v_b1':                dict(B=1, H=1, W=4096, C=[256], taps=[1], N=4096, flags=0),
+    'v_n1024':             dict(B=2, H=1, W=4096, C=[256], taps=[1], N=1024, flags=0),
+    'v_n512':              dict(B=2, H=1, W=4096, C=[256], taps=[1], N=512, flags=0),
+    'v_w2048':             dict(B=2, H=1, W=2048, C=[256], taps=[1], N=2048, flags=0),
+    'v_k64':               dict(B=2, H=1, W=4096, C=[64], taps=[1], N=4096, flags=0),
+    'v_b1_st1':            dict(B=1, H=1, W=4096, C=[256], taps=[1], N=4096, flags=256),
+    'v_b1_a4':             dict(B=1, H=1, W=4096, C=[256], taps=[1], N=4096, flags=512),
+    'v_b1_k128':           dict(B=1, H=1, W=4096, C=[128], taps=[1], N=4096, flags=0),
+    'gemm_ntiles4':        dict(B=1, H=1, W=1024, C=[256], taps=[1], N=1024, flags=0),
+    'gemm_ntiles16_b2':    dict(B=2, H=1, W=4096, C=[256], taps=[1], N=4096, flags=0),
+    'conv_multiunit_bias': dict(B=4, H=128, W=128, C=[64], taps=[9], N=64, flags=0, epi=True),
     'many_tiles':          dict(B=8, H=64, W=64, C=[64], taps=[9], N=64, flags=0),
     'many_tiles_n128':     dict(B=8, H=64, W=64, C=[128], taps=[9], N=128, flags=0),
 }
@@ -35,6 +53,7 @@ def run_case(name):
     import mudiff_b200 as M
     from mudiff_b200 import ops
     c = CASES[name]
+    print('   debug channel selftest:', M._lib.lib().mudiff_debug_selftest(), flush=True)
     torch.manual_seed(0)
     dev = 'cuda'
     B, H, W, N = c['B'], c['H'], c['W'], c['N']
@@ -57,8 +76,12 @@ def run_case(name):
     if c.get('act') == 2:
         ref = torch.sigmoid(ref)
         kw['act'] = 2
-    out = ops.conv(segs, wt, N, out_dtype=torch.float32, flags=c['flags'], force='tc', **kw)
     torch.cuda.synchronize()
+    print('   launching f32-out conv', flush=True)
+    out = ops.conv(segs, wt, N, out_dtype=torch.float32, flags=c['flags'], force='tc', **kw)
+    print('   launched', flush=True)
+    torch.cuda.synchronize()
+    print('   f32-out conv done', flush=True)
     err = (out - ref).abs().max().item()
     scale = ref.abs().max().item()
     # bf16 output too
@@ -82,7 +105,16 @@ def run_case(name):
 
 if __name__ == '__main__':
     if len(sys.argv) > 1:
-        sys.exit(run_case(sys.argv[1]))
+        try:
+            rc = run_case(sys.argv[1])
+        except Exception as e:
+            import ctypes
+            import mudiff_b200 as M
+            info = (ctypes.c_int32 * 8)()
+            M._lib.lib().mudiff_debug_last_timeout(info)
+            print('EXCEPTION', type(e).__name__, str(e).splitlines()[0], ' timeout-info', list(info), flush=True)
+            rc = 2
+        sys.exit(rc)
     fails = 0
     for name in CASES:
         t0 = time.time()
