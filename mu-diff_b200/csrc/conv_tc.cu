@@ -23,7 +23,9 @@
 namespace {
 
 constexpr int kMaxSlots = 16;
-constexpr int kThreads = 352;               // 3 producer/MMA warps + 8 epilogue warps
+constexpr int kThreads = 256;               // warps 0-2: A producer, B producer, MMA; warp 3 idle; warps 4-7: epilogue.
+// One epilogue warp per TMEM lane quadrant.  Two warps per quadrant (8 epilogue warps, aligned or not) made
+// epilogue-bound GEMMs (N = 4096, K = 256) fault intermittently on B200 (~1 launch in 10, tools/stress_conv.py).
 constexpr uint32_t kSmemMax = 232448;       // 227 KB opt-in limit per CTA
 
 struct TcParams {
@@ -213,7 +215,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -375,11 +377,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (p.acc_stages == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
       __syncwarp();
     }
-  } else {
+  } else if (warp >= 4) {
     // =========================== epilogue ===============================
     const int q = warp & 3;                        // TMEM lane quadrant this warp may read
-    const int half = (warp - 3) >> 2;              // two warps share a lane quadrant: even / odd 32-column chunks
-    const int et = (warp - 3) * 32 + lane;         // epilogue thread index 0..255
+    const int et = (warp - 4) * 32 + lane;         // epilogue thread index 0..127
     const int row = q * 32 + lane;                 // accumulator row == pixel within the tile
     const int ty_in = row / p.tile_w, tx_in = row - ty_in * p.tile_w;
     float* sstat = (float*)(smem + p.off_stats);   // [4 quadrants][n_tile][2]
@@ -389,14 +390,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (long long u = u_begin; u < u_end; u += u_step) {
       const Unit un = decode_unit(p, u);
       if ((p.bias || p.rowbias) && (un.b != bias_b || un.n0 != bias_n0)) {
-        // stage bias[n] + rowbias[b][n] once per (image, N tile); all 256 epilogue threads take part
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        for (int col = et; col < p.n_tile; col += 256) {
+        // stage bias[n] + rowbias[b][n] once per (image, N tile); all 128 epilogue threads take part
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        for (int col = et; col < p.n_tile; col += 128) {
           float bv = p.bias ? __ldg(p.bias + un.n0 + col) : 0.f;
           if (p.rowbias) bv += __ldg(p.rowbias + (int64_t)un.b * p.rowbias_ld + un.n0 + col);
           sbias[col] = bv;
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
+        asm volatile("bar.sync 2, 128;" ::: "memory");
         bias_b = un.b; bias_n0 = un.n0;
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -408,7 +409,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const bool valid = (y < p.H) && (x < p.W);
         const int64_t pix = ((int64_t)un.b * p.H + y) * p.W + x;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.MT + m) * p.acc_stride);
-        for (int c = half * 32; c < p.n_tile; c += 64) {
+        for (int c = 0; c < p.n_tile; c += 32) {
           uint32_t v[32];
           tmem_ld32(taddr0 + (uint32_t)c, v);
           tmem_ld_wait();
@@ -494,9 +495,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
         if (p.stats_partial) {
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
           float* dst = p.stats_partial + (((int64_t)un.b * p.tpi + r) * p.n_total + un.n0) * 2;
-          for (int col = et; col < p.n_tile; col += 256) {
+          for (int col = et; col < p.n_tile; col += 128) {
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
@@ -505,7 +506,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             *reinterpret_cast<float2*>(dst + col * 2) = make_float2(s0, s1);
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
       tc_fence_before();
