@@ -89,12 +89,25 @@ class _Proxy:
 
     @staticmethod
     def _wrap(name, fn):
+        sync_ops = os.environ.get('MUDIFF_SYNC', '')       # debug: "all" or comma-separated entry points
+        do_sync = sync_ops == 'all' or name in sync_ops.split(',')
+        counter = [0]
+
         def call(*args):
             prof = _CALL_PROFILER
             if prof is None:
-                return fn(*args)
-            with prof(name):
-                return fn(*args)
+                rc = fn(*args)
+            else:
+                with prof(name):
+                    rc = fn(*args)
+            if do_sync and name not in ('mudiff_debug_last_timeout', 'mudiff_debug_selftest', 'mudiff_conv_tc_query'):
+                counter[0] += 1
+                try:
+                    torch.cuda.synchronize()
+                except Exception as e:
+                    raise RuntimeError(f"mu-diff_b200: device error detected right after {name} call #{counter[0]}: "
+                                       f"{str(e).splitlines()[0]}") from None
+            return rc
         return call
 
 
