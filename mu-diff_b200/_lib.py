@@ -85,7 +85,10 @@ class _Proxy:
     def __init__(self, cdll):
         self._cdll = cdll
         for name in PROTOTYPES:
-            setattr(self, name, self._wrap(name, getattr(cdll, name)))
+            if hasattr(cdll, name):
+                setattr(self, name, self._wrap(name, getattr(cdll, name)))
+            else:                                   # only possible with MUDIFF_LIB (older debug builds)
+                setattr(self, name, lambda *a: 0)
 
     @staticmethod
     def _wrap(name, fn):
@@ -119,12 +122,15 @@ def lib():
             raise RuntimeError(
                 f"mu-diff_b200: {LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or `make -C mu-diff_b200/csrc`). There is no CPU fallback.")
-        l = C.CDLL(LIB_PATH)
+        alt = os.environ.get('MUDIFF_LIB')          # debug only: bisecting older builds of the library
+        l = C.CDLL(os.path.abspath(alt) if alt else LIB_PATH)
         for name, argtypes in PROTOTYPES.items():
+            if alt and not hasattr(l, name):
+                continue
             fn = getattr(l, name)           # AttributeError if the .so does not export a declared symbol
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if l.mudiff_conv_desc_size() != C.sizeof(ConvDesc):
+        if not alt and l.mudiff_conv_desc_size() != C.sizeof(ConvDesc):
             raise RuntimeError('mu-diff_b200: ConvDesc layout mismatch between _lib.py and the shared library')
         _lib = _Proxy(l)
     return _lib

@@ -43,7 +43,7 @@ struct TcParams {
   int acc_stride, acc_stages, tmem_cols;
   int base_off_variant;
   int round_robin;                            // debug: interleaved instead of contiguous unit assignment
-  int dbg_dry, dbg_noepi;                     // debug: no operand traffic / no epilogue work (timing only)
+  int dbg_dry, dbg_noepi, dbg_nostore, dbg_noldtm, dbg_sleep_mma, dbg_sleep_epi;                     // debug: no operand traffic / no epilogue work (timing only)
   // epilogue
   const float* bias; const float* rowbias; int rowbias_ld;
   const void* residual; int res_ld;
@@ -297,8 +297,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else if (warp == 2) {
     // =========================== MMA issuer =============================
     // The issue rate of this single warp bounds every N <= 192 shape (UMMA 128xNx16 needs < 100 clk of
-    // tensor time), so the loop is kept as lean as possible: lane 0 polls the mbarriers, the warp
-    // re-converges, descriptor low words are precomputed per group and advanced with immediates.
+    // tensor time), so the loop is kept as lean as possible: all lanes poll the mbarriers (warp-uniform
+    // control flow), descriptor low words are precomputed per group and advanced with immediates.
     const bool leader = elect_one();
     uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
@@ -310,12 +310,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t a_lo_base = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t a_step = p.a_slot_bytes >> 4;
     const bool dry = p.dbg_dry != 0;
-    if (p.stationary && !dry) { if (leader) mbar_wait(w_full, 0); __syncwarp(); tc_fence_after(); }
+    if (p.stationary && !dry) { mbar_wait(w_full, 0); tc_fence_after(); }
     for (long long u = u_begin; u < u_end; u += u_step) {
       const Unit un = decode_unit(p, u);
-      if (leader) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      __syncwarp();
-      tc_fence_after();
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // ALL lanes poll: leader-only polling + __syncwarp
+      tc_fence_after();                                    // deadlocked / faulted intermittently on B200
       uint32_t accum = 0;                                  // 0 only for the first MMA of each accumulator
       const uint32_t d0 = tmem_base + (uint32_t)((acc * p.MT) * p.acc_stride);
       const uint32_t d1 = d0 + (uint32_t)p.acc_stride;
@@ -325,8 +324,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint32_t sl0 = a_slot;
         uint32_t sl1 = a_slot + 1, ph1 = a_phase;
         if (sl1 == (uint32_t)p.a_slots) { sl1 = 0; ph1 ^= 1u; }
-        if (leader && !dry) { mbar_wait(&a_full[sl0], a_phase); if (two) mbar_wait(&a_full[sl1], ph1); }
-        __syncwarp();
+        if (!dry) { mbar_wait(&a_full[sl0], a_phase); if (two) mbar_wait(&a_full[sl1], ph1); }
         tc_fence_after();
         const uint32_t alo0 = a_lo_base + sl0 * a_step;
         const uint32_t alo1 = a_lo_base + sl1 * a_step;
@@ -340,8 +338,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (p.stationary) {
               blo = b_lo_base + (uint32_t)(kbase + j * kstep) * b_step;
             } else {
-              if (leader && !dry) mbar_wait(&b_full[b_slot], b_phase);
-              __syncwarp();
+              if (!dry) mbar_wait(&b_full[b_slot], b_phase);
               tc_fence_after();
               blo = b_lo_base + b_slot * b_step;
             }
@@ -411,13 +408,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.MT + m) * p.acc_stride);
         for (int c = 0; c < p.n_tile; c += 32) {
           uint32_t v[32];
-          tmem_ld32(taddr0 + (uint32_t)c, v);
-          tmem_ld_wait();
+          if (!p.dbg_noldtm) { tmem_ld32(taddr0 + (uint32_t)c, v); tmem_ld_wait(); }
+          else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
           const int n = un.n0 + c;
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (valid) {
+          if (valid && !p.dbg_nostore) {
             if (p.bias || p.rowbias) {
               const float4* sb4 = reinterpret_cast<const float4*>(sbias + c);
 #pragma unroll
@@ -685,6 +685,10 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   p.round_robin = (d->flags & 32) ? 1 : 0;
   p.dbg_dry = (d->flags & 64) ? 1 : 0;
   p.dbg_noepi = (d->flags & 128) ? 1 : 0;
+  p.dbg_nostore = (d->flags & 2048) ? 1 : 0;
+  p.dbg_noldtm = (d->flags & 4096) ? 1 : 0;
+  p.dbg_sleep_mma = (d->flags & 8192) ? 1 : 0;
+  p.dbg_sleep_epi = (d->flags & 16384) ? 1 : 0;
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
   p.residual = d->residual; p.res_ld = d->res_ld; p.alpha = d->alpha; p.beta = d->beta; p.act = d->act;
   p.out = d->out; p.out_ld = d->out_ld; p.out_coff = d->out_coff;
