@@ -154,7 +154,10 @@ typedef struct mudiff_conv_desc {
                            /*   (sum,sumsq) of the OUTPUT; stats_groups is unused   */
   int32_t flags;           /* debug/ablation: bit1 forbid halo staging, bit2 descriptor
                               base-offset variant, bit3 forbid stationary weights,
-                              bit4 one pixel tile per unit                          */
+                              bit4 one pixel tile per unit.  bit15 (0x8000): decimate - keep only the
+                              odd (y, x) outputs of the 'same' 3x3 conv and write them at ((y-1)/2,
+                              (x-1)/2) of an [(h-1)/2, (w-1)/2] output: this IS the stride-2 VALID conv
+                              of conv_downsample_2d (up_or_down_sampling.py:183) on the tensor cores */
 } mudiff_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit GEMM (bf16 in, fp32 accumulate).  Requires a_c[i] % 64 == 0,

@@ -216,11 +216,10 @@ __global__ void __launch_bounds__(256) conv_small_k_kernel(SimtP p) {
 // HBM-write bound (9 MACs per output).  One block per output row; a thread owns 8 output channels
 // (72 weights + 8 biases in registers) and walks the row; a warp stores 4 pixels x 128 B contiguous.
 // ---------------------------------------------------------------------------------
+#define STEM_ROWS 8
 template <typename TO>
 __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
   const int nv = p.n / 8;
-  const int row = blockIdx.x;                 // b * H + y
-  const int b = row / p.h, y = row - b * p.h;
   const int n0 = (threadIdx.x % nv) * 8;
   const int lane = threadIdx.x / nv, lanes = blockDim.x / nv;
   if (lane >= lanes) return;
@@ -231,10 +230,16 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
 #pragma unroll
     for (int t = 0; t < 9; ++t) w[t][j] = wt[(n0 + j) * 9 + t];
     bs[j] = p.bias ? p.bias[n0 + j] : 0.f;
-    if (p.rowbias) bs[j] += p.rowbias[(int64_t)b * p.rowbias_ld + n0 + j];
   }
-  const float* in = (const float*)p.a[0] + (int64_t)b * p.h * p.w * p.a_ld[0];
   const int ld = p.a_ld[0];
+  const int64_t rows = (int64_t)p.batch * p.h;
+  // STEM_ROWS consecutive rows per block amortise the 80 weight/bias loads of every thread
+  for (int64_t row = (int64_t)blockIdx.x * STEM_ROWS; row < rows && row < (int64_t)(blockIdx.x + 1) * STEM_ROWS; ++row) {
+  const int b = (int)(row / p.h), y = (int)(row - (int64_t)b * p.h);
+  float rb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) rb[j] = bs[j] + (p.rowbias ? p.rowbias[(int64_t)b * p.rowbias_ld + n0 + j] : 0.f);
+  const float* in = (const float*)p.a[0] + (int64_t)b * p.h * p.w * ld;
   for (int x = lane; x < p.w; x += lanes) {
     float v[9];
 #pragma unroll
@@ -248,9 +253,9 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
       float a = 0.f;
 #pragma unroll
       for (int t = 0; t < 9; ++t) a = fmaf(v[t], w[t][j], a);
-      acc[j] = apply_act((a + bs[j]) * p.alpha, p.act);
+      acc[j] = apply_act((a + rb[j]) * p.alpha, p.act);
     }
-    const int64_t pix = (int64_t)row * p.w + x;
+    const int64_t pix = row * p.w + x;
     TO* op = (TO*)p.out + pix * p.out_ld + p.out_coff + n0;
     if constexpr (sizeof(TO) == 2) {
       store_vec<TO>(op, acc);
@@ -260,6 +265,7 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
       store_vec<float>((float*)op + 4, hi);
     }
   }
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -268,36 +274,54 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
 // 8 lanes per pixel, each lane reads one 16-byte channel vector per tap (coalesced 128 B per pixel-tap),
 // weights of the lane's channels in registers, 3 shuffles to reduce.  One block per output row.
 // ---------------------------------------------------------------------------------
+#define HEAD_ROWS 4
 template <typename TA, typename TO>
 __global__ void __launch_bounds__(256) conv_head_kernel(SimtP p) {
   constexpr int V = 16 / sizeof(TA);          // 8 (bf16) or 4 (fp32) channels per load
   constexpr int LPP = 64 / V;                 // lanes per pixel for one 64-channel block: 8 or 16
-  const int row = blockIdx.x;
-  const int b = row / p.h, y = row - b * p.h;
   const int sub = threadIdx.x % LPP;
   const int lane = threadIdx.x / LPP, lanes = blockDim.x / LPP;
   const int C = p.a_c[0];
   const int ld = p.a_ld[0];
-  const TA* in = (const TA*)p.a[0] + (int64_t)b * p.h * p.w * ld;
   const TA* wt = (const TA*)p.wt;
-  for (int x = lane; x < p.w; x += lanes) {
-    float acc = 0.f;
-    for (int cb = 0; cb < C; cb += 64) {
-      const int c = cb + sub * V;
+  const bool one_block = C == 64;
+  float wreg[9][V];                           // weights of this lane's channels (first 64-channel block)
+#pragma unroll
+  for (int t = 0; t < 9; ++t) load_vec<TA>(wt + t * C + sub * V, wreg[t]);
+  const int64_t rows = (int64_t)p.batch * p.h;
+  for (int64_t row = (int64_t)blockIdx.x * HEAD_ROWS; row < rows && row < (int64_t)(blockIdx.x + 1) * HEAD_ROWS; ++row) {
+    const int b = (int)(row / p.h), y = (int)(row - (int64_t)b * p.h);
+    const TA* in = (const TA*)p.a[0] + (int64_t)b * p.h * p.w * ld;
+    for (int x = lane; x < p.w; x += lanes) {
+      float acc = 0.f;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
         if (iy < 0 || iy >= p.h || ix < 0 || ix >= p.w) continue;
-        float v[V], w[V];
-        load_vec<TA>(in + ((int64_t)iy * p.w + ix) * ld + c, v);
-        load_vec<TA>(wt + t * C + c, w);       // packed k = tap*C + c ; L1-resident
+        float v[V];
+        load_vec<TA>(in + ((int64_t)iy * p.w + ix) * ld + sub * V, v);
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc = fmaf(v[k], w[k], acc);
+        for (int k = 0; k < V; ++k) acc = fmaf(v[k], wreg[t][k], acc);
       }
-    }
+      if (!one_block) {
+        for (int cb = 64; cb < C; cb += 64) {
+          const int c = cb + sub * V;
 #pragma unroll
-    for (int o = LPP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (sub == 0) epilogue_store<TO>(p, b, (int64_t)row * p.w + x, 0, acc);
+          for (int t = 0; t < 9; ++t) {
+            const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
+            if (iy < 0 || iy >= p.h || ix < 0 || ix >= p.w) continue;
+            float v[V], w[V];
+            load_vec<TA>(in + ((int64_t)iy * p.w + ix) * ld + c, v);
+            load_vec<TA>(wt + t * C + c, w);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc = fmaf(v[k], w[k], acc);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (sub == 0) epilogue_store<TO>(p, b, row * p.w + x, 0, acc);
+    }
   }
 }
 
@@ -312,13 +336,13 @@ int launch_simt(const SimtP& p, cudaStream_t st) {
         (p.out_ld % 8 == 0) && (p.out_coff % 8 == 0)) {
       const int nv = p.n / 8;
       int block = (256 / nv) * nv;
-      conv_stem_kernel<TO><<<(unsigned)rows, block, 0, st>>>(p);
+      conv_stem_kernel<TO><<<(unsigned)((rows + STEM_ROWS - 1) / STEM_ROWS), block, 0, st>>>(p);
       return mudiff_launch_status();
     }
   }
   if (plain && s1 && p.n == 1 && p.a_c[0] % 64 == 0 && p.a_ld[0] % (16 / (int)sizeof(TA)) == 0 && rows < (1LL << 31) &&
       ((uintptr_t)p.a[0] % 16 == 0) && ((uintptr_t)p.wt % 16 == 0)) {
-    conv_head_kernel<TA, TO><<<(unsigned)rows, 256, 0, st>>>(p);
+    conv_head_kernel<TA, TO><<<(unsigned)((rows + HEAD_ROWS - 1) / HEAD_ROWS), 256, 0, st>>>(p);
     return mudiff_launch_status();
   }
   if (plain && p.n <= 4 && (size_t)p.n * p.ktot * 4 <= 48 * 1024) {

@@ -43,7 +43,8 @@ struct TcParams {
   int acc_stride, acc_stages, tmem_cols;
   int base_off_variant;
   int round_robin;                            // debug: interleaved instead of contiguous unit assignment
-  int dbg_dry, dbg_noepi, dbg_nostore, dbg_noldtm, dbg_sleep_mma, dbg_sleep_epi;                     // debug: no operand traffic / no epilogue work (timing only)
+  int dbg_dry, dbg_noepi, dbg_nostore, dbg_noldtm;
+  int dec2, Ho, Wo;                           // stride-2 VALID conv as a decimated 'same' conv: keep odd (y, x) only                     // debug: no operand traffic / no epilogue work (timing only)
   // epilogue
   const float* bias; const float* rowbias; int rowbias_ld;
   const void* residual; int res_ld;
@@ -403,8 +404,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int r = un.r0 + m;
         const int tyt = r / p.tiles_x;
         const int y = tyt * p.tile_h + ty_in, x = (r - tyt * p.tiles_x) * p.tile_w + tx_in;
-        const bool valid = (y < p.H) && (x < p.W);
-        const int64_t pix = ((int64_t)un.b * p.H + y) * p.W + x;
+        bool valid = (y < p.H) && (x < p.W);
+        int64_t pix = ((int64_t)un.b * p.H + y) * p.W + x;
+        if (p.dec2) {
+          valid = valid && (y & 1) && (x & 1) && (y >> 1) < p.Ho && (x >> 1) < p.Wo;
+          pix = ((int64_t)un.b * p.Ho + (y >> 1)) * p.Wo + (x >> 1);
+        }
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.MT + m) * p.acc_stride);
         for (int c = 0; c < p.n_tile; c += 32) {
           uint32_t v[32];
@@ -687,8 +692,9 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   p.dbg_noepi = (d->flags & 128) ? 1 : 0;
   p.dbg_nostore = (d->flags & 2048) ? 1 : 0;
   p.dbg_noldtm = (d->flags & 4096) ? 1 : 0;
-  p.dbg_sleep_mma = (d->flags & 8192) ? 1 : 0;
-  p.dbg_sleep_epi = (d->flags & 16384) ? 1 : 0;
+  p.dec2 = (d->flags & 32768) ? 1 : 0;
+  p.Ho = p.dec2 ? (d->h - 1) / 2 : d->h;
+  p.Wo = p.dec2 ? (d->w - 1) / 2 : d->w;
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
   p.residual = d->residual; p.res_ld = d->res_ld; p.alpha = d->alpha; p.beta = d->beta; p.act = d->act;
   p.out = d->out; p.out_ld = d->out_ld; p.out_coff = d->out_coff;

@@ -212,7 +212,7 @@ def tc_eligible(segs, n, stride, dtype) -> bool:
 
 def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta=0.0, act=L.ACT_NONE,
          out=None, out_coff=0, out_dtype=None, stride=1, pad=1, w_bstride=0, w_ld=0, a_batched=True,
-         batch=None, flags=0, force=None, want_stats=False, stats_out=None):
+         batch=None, flags=0, force=None, want_stats=False, stats_out=None, dec2=False):
     """Implicit-GEMM convolution.  segs = [(tensor NCHW-logical/channels-last, taps)], wt packed K-major.
     Chooses the tcgen05 kernel when eligible (bf16, Cin % 64 == 0, N % 32 == 0, stride 1), otherwise the
     CUDA-core kernel.  `force` in {None,'tc','simt'}."""
@@ -220,7 +220,10 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
     dev = x0.device
     b = batch if batch is not None else x0.shape[0]
     h, w = x0.shape[2], x0.shape[3]
-    if stride == 1:
+    if dec2:                      # stride-2 VALID 3x3 conv == odd outputs of the pad-1 'same' conv (tensor-core path)
+        ho, wo = (h - 1) // 2, (w - 1) // 2
+        flags |= 0x8000
+    elif stride == 1:
         ho, wo = h, w
     else:
         k = 3 if any(t == 9 for _, t in segs) else 1

@@ -71,6 +71,11 @@ def conv_downsample_2d(x, w, k=None, factor=2, gain=1, _packed=None, _bias=None,
     p = (k.shape[0] - factor) + (convW - 1)
     x = _fir(x, k, pad=((p + 1) // 2, p // 2))
     wt = _packed if _packed is not None else ops.pack_conv_weight(w, (_inC,), x.dtype)
+    if (factor == 2 and convH == 3 and x.dtype == torch.bfloat16 and _inC % 64 == 0 and _outC % 32 == 0
+            and x.shape[2] % 2 == 1 and x.shape[3] % 2 == 1):
+        # tensor-core path: 'same' conv, keep the odd outputs (4x the FLOPs of the strided conv, still ~8x faster
+        # than the CUDA-core kernel: K = 576 is far too small to matter next to the 3x3 convs of the level)
+        return ops.conv([(x, 9)], wt, _outC, bias=_bias, pad=1, dec2=True, out_dtype=_out_dtype)
     return ops.conv([(x, convH * convW)], wt, _outC, bias=_bias, stride=factor, pad=0, force='simt',
                     out_dtype=_out_dtype)
 

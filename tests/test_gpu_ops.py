@@ -234,6 +234,23 @@ def test_conv_tc_vs_fp32_reference(M, name):
         np.testing.assert_allclose(cs[..., 1].numpy(), (o64 ** 2).sum(dim=(2, 3)).numpy(), rtol=1e-5, atol=1e-3)
 
 
+def test_conv_tc_decimated_equals_stride2_valid(M):
+    """conv_downsample_2d's stride-2 VALID 3x3 conv (up_or_down_sampling.py:183) on the tensor cores:
+    odd outputs of the pad-1 'same' conv."""
+    from mudiff_b200 import ops
+    torch.manual_seed(3)
+    x = torch.randn(3, 64, 33, 33).to(torch.bfloat16)
+    w = (torch.randn(128, 64, 3, 3) / 24).to(torch.bfloat16)
+    bias = torch.randn(128)
+    ref = F.conv2d(x.float(), w.float(), bias, stride=2, padding=0)
+    y = ops.conv([(ops.as_nhwc(x.cuda()), 9)], ops.pack_conv_weight(w.cuda(), (64,), torch.bfloat16), 128,
+                 bias=bias.cuda(), pad=1, dec2=True, out_dtype=torch.float32, want_stats=True)
+    assert tuple(y.shape) == tuple(ref.shape) == (3, 128, 16, 16)
+    assert (y.cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    cs = ops.get_chstats(y).cpu()
+    np.testing.assert_allclose(cs[..., 0].numpy(), y.double().cpu().sum(dim=(2, 3)).numpy(), rtol=1e-5, atol=1e-3)
+
+
 def test_conv_tc_batched_weights_qk(M):
     """S[b] = Q[b] K[b]^T * alpha with K taken from a [B, L, 2C] buffer (w_ld, w_bstride)."""
     from mudiff_b200 import ops
