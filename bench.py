@@ -44,6 +44,29 @@ def peaks():
     return dict(tf_sustained=1400.0, tf_burst=1590.0, hbm=6650.0, src='fallback')
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch from the committed `ncu --set full`
+    capture (profiles/r01_ncu_conv_tc_full_summary.json); None if the capture is not there."""
+    p = os.path.join(ROOT, 'profiles', 'r01_ncu_conv_tc_full_summary.json')
+    if not os.path.exists(p):
+        return None, "no ncu --set full capture committed"
+    tot, n = 0.0, 0
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for rec in json.load(open(p)):
+        try:
+            b = 0.0
+            for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                v, u = rec[k].split()
+                b += float(v) * scale.get(u, 1.0)
+            tot += b
+            n += 1
+        except Exception:
+            pass
+    if not n:
+        return None, "capture unreadable"
+    return tot / n, f"mean DRAM bytes per conv_tc launch over the {n} launches of the committed capture (taken at batch 8; launch shapes differ)"
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
@@ -331,8 +354,10 @@ def main():
         tc_flops = sum(r.flops for r in tc)
         simt_ms = sum(r.a.elapsed_time(r.b) for r in recs if r.kind == 'conv_simt')
         ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        traffic, traffic_note = ncu_traffic()
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "achieved": ach,
-                "peak": pk['tf_sustained'], "unit": "TFLOP/s", "frac": ach / pk['tf_sustained'], "traffic": None,
+                "peak": pk['tf_sustained'], "unit": "TFLOP/s", "frac": ach / pk['tf_sustained'], "traffic": traffic,
+                "traffic_note": traffic_note,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
                 "launches": len(tc), "kernel_ms_per_step": tc_ms, "share_of_step": tc_ms / (ms_max / args.steps),
                 "algorithmic_tflop_per_step": tc_flops / 1e12, "conv_simt_ms_per_step": simt_ms}
