@@ -23,7 +23,7 @@
 namespace {
 
 constexpr int kMaxSlots = 16;
-constexpr int kThreads = 256;               // warps 0-2: A producer, B producer, MMA; warp 3 idle; warps 4-7: epilogue.
+constexpr int kThreads = 256;               // warps 0-3: A producer, B producer, MMA issuer of tile 0, MMA issuer of tile 1; warps 4-7: epilogue.
 // One epilogue warp per TMEM lane quadrant.  Two warps per quadrant (8 epilogue warps, aligned or not) made
 // epilogue-bound GEMMs (N = 4096, K = 256) fault intermittently on B200 (~1 launch in 10, tools/stress_conv.py).
 constexpr uint32_t kSmemMax = 232448;       // 227 KB opt-in limit per CTA
@@ -214,9 +214,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < p.b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.MT); }     // one arrival per issuing warp
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], p.MT); mbar_init(&tempty_bar[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -295,11 +295,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
       }
     }
-  } else if (warp == 2) {
-    // =========================== MMA issuer =============================
-    // The issue rate of this single warp bounds every N <= 192 shape (UMMA 128xNx16 needs < 100 clk of
-    // tensor time), so the loop is kept as lean as possible: all lanes poll the mbarriers (warp-uniform
-    // control flow), descriptor low words are precomputed per group and advanced with immediates.
+  } else if (warp == 2 || (warp == 3 && p.MT == 2)) {
+    // =========================== MMA issuers =============================
+    // The single-thread issue rate bounds every N <= 192 shape (UMMA 128xNx16 needs < 100 clk of tensor
+    // time), so (1) the loop is kept lean: all lanes poll the mbarriers (warp-uniform control flow; polling
+    // by the elected lane alone + __syncwarp deadlocked / faulted intermittently on B200), descriptor low
+    // words are precomputed per group and advanced with immediates; (2) with two pixel tiles per unit
+    // there are TWO issuing warps: warp 2 owns tile 0 and its accumulator, warp 3 owns tile 1.  A weight
+    // sub-tile is released when both have committed (b_empty / tfull expect two arrivals).
+    const int me = warp - 2;                               // which pixel tile of the unit this warp issues
     const bool leader = elect_one();
     uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
@@ -314,21 +318,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (p.stationary && !dry) { mbar_wait(w_full, 0); tc_fence_after(); }
     for (long long u = u_begin; u < u_end; u += u_step) {
       const Unit un = decode_unit(p, u);
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // ALL lanes poll: leader-only polling + __syncwarp
-      tc_fence_after();                                    // deadlocked / faulted intermittently on B200
-      uint32_t accum = 0;                                  // 0 only for the first MMA of each accumulator
-      const uint32_t d0 = tmem_base + (uint32_t)((acc * p.MT) * p.acc_stride);
-      const uint32_t d1 = d0 + (uint32_t)p.acc_stride;
-      const bool two = un.count > 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      uint32_t accum = 0;                                  // 0 only for the first MMA of the accumulator
+      const uint32_t d_mine = tmem_base + (uint32_t)((acc * p.MT + me) * p.acc_stride);
+      const bool active = me < un.count;                   // partial last group of an image: tile 1 may not exist
       for_each_group(p, [&](int s, int cb, int tap, int nb) {
-        // A tiles of this group (one or two pixel tiles)
-        const uint32_t sl0 = a_slot;
-        uint32_t sl1 = a_slot + 1, ph1 = a_phase;
-        if (sl1 == (uint32_t)p.a_slots) { sl1 = 0; ph1 ^= 1u; }
-        if (!dry) { mbar_wait(&a_full[sl0], a_phase); if (two) mbar_wait(&a_full[sl1], ph1); }
+        // my A tile of this group
+        uint32_t sl = a_slot + (uint32_t)me, ph = a_phase;
+        if (sl >= (uint32_t)p.a_slots) { sl -= (uint32_t)p.a_slots; ph ^= 1u; }
+        if (active && !dry) mbar_wait(&a_full[sl], ph);
         tc_fence_after();
-        const uint32_t alo0 = a_lo_base + sl0 * a_step;
-        const uint32_t alo1 = a_lo_base + sl1 * a_step;
+        const uint32_t alo = a_lo_base + sl * a_step;
         const uint32_t hi_a = nb == 9 ? hi_a_halo : hi_b;
         const int kbase = (p.seg_koff[s] + (nb == 9 ? 0 : tap) * p.seg_c[s]) / 64 + cb;   // stationary sub-tile index of tap 0
         const int kstep = p.seg_c[s] / 64;                                                   // ... and its stride per tap
@@ -345,33 +346,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             const uint32_t toff = (uint32_t)((j / 3) * 10 + (j % 3)) * 8u;     // tap offset in 16-byte units (halo only; j == 0 otherwise)
             if (leader) {
-              const uint64_t bd = ((uint64_t)hi_b << 32) | blo;
-              const uint64_t ad = ((uint64_t)hi_a << 32) | (alo0 + toff);
-              tc_mma_f16(d0, ad, bd, p.idesc, accum);
-              tc_mma_f16(d0, ad + 2, bd + 2, p.idesc, 1u);
-              tc_mma_f16(d0, ad + 4, bd + 4, p.idesc, 1u);
-              tc_mma_f16(d0, ad + 6, bd + 6, p.idesc, 1u);
-              if (two) {
-                const uint64_t ae = ((uint64_t)hi_a << 32) | (alo1 + toff);
-                tc_mma_f16(d1, ae, bd, p.idesc, accum);
-                tc_mma_f16(d1, ae + 2, bd + 2, p.idesc, 1u);
-                tc_mma_f16(d1, ae + 4, bd + 4, p.idesc, 1u);
-                tc_mma_f16(d1, ae + 6, bd + 6, p.idesc, 1u);
+              if (active) {
+                const uint64_t bd = ((uint64_t)hi_b << 32) | blo;
+                const uint64_t ad = ((uint64_t)hi_a << 32) | (alo + toff);
+                tc_mma_f16(d_mine, ad, bd, p.idesc, accum);
+                tc_mma_f16(d_mine, ad + 2, bd + 2, p.idesc, 1u);
+                tc_mma_f16(d_mine, ad + 4, bd + 4, p.idesc, 1u);
+                tc_mma_f16(d_mine, ad + 6, bd + 6, p.idesc, 1u);
               }
-              if (!p.stationary) tc_commit(&b_empty[b_slot]);
+              if (!p.stationary) tc_commit(&b_empty[b_slot]);       // one arrival per issuing warp
             }
             if (!p.stationary) { if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_phase ^= 1u; } }
             accum = 1u;
           }
         }
-        if (leader) {                                         // both A tiles are free once the last tap retires
-          tc_commit(&a_empty[sl0]);
-          if (two) tc_commit(&a_empty[sl1]);
-        }
+        if (leader && active) tc_commit(&a_empty[sl]);              // my A tile is free once its last tap retires
         a_slot += (uint32_t)un.count;
         if (a_slot >= (uint32_t)p.a_slots) { a_slot -= (uint32_t)p.a_slots; a_phase ^= 1u; }
       });
-      if (leader) tc_commit(&tfull_bar[acc]);                // accumulators complete -> epilogue
+      if (leader) tc_commit(&tfull_bar[acc]);                // my accumulator is complete -> epilogue
       if (p.acc_stages == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
       __syncwarp();
     }
