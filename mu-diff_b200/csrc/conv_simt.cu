@@ -212,11 +212,11 @@ __global__ void __launch_bounds__(256) conv_small_k_kernel(SimtP p) {
 
 
 // ---------------------------------------------------------------------------------
-// stem kernel: Cin == 1, 3x3 pad 1, stride 1, N % 8 == 0 (the 1->nf ConvFeatBlock convs).
-// HBM-write bound (9 MACs per output).  One block per output row; a thread owns 8 output channels
-// (72 weights + 8 biases in registers) and walks the row; a warp stores 4 pixels x 128 B contiguous.
-// ---------------------------------------------------------------------------------
 #define STEM_ROWS 8
+// stem kernel: Cin == 1, 3x3 pad 1, stride 1, N % 8 == 0 (the 1->nf ConvFeatBlock convs).
+// HBM-write bound in principle (9 MACs per output) but FFMA/issue bound in practice, so every thread
+// computes TWO adjacent pixels x 8 output channels from one 3x4 input patch (12 loads for 144 FMAs; the 72
+// weights + 8 biases live in registers), STEM_ROWS rows per block; a warp stores 8 pixels x 128 B contiguous.
 template <typename TO>
 __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
   const int nv = p.n / 8;
@@ -232,39 +232,49 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
     bs[j] = p.bias ? p.bias[n0 + j] : 0.f;
   }
   const int ld = p.a_ld[0];
-  const int64_t rows = (int64_t)p.batch * p.h;
-  // STEM_ROWS consecutive rows per block amortise the 80 weight/bias loads of every thread
+  const int W = p.w, H = p.h;
+  const int64_t rows = (int64_t)p.batch * H;
   for (int64_t row = (int64_t)blockIdx.x * STEM_ROWS; row < rows && row < (int64_t)(blockIdx.x + 1) * STEM_ROWS; ++row) {
-  const int b = (int)(row / p.h), y = (int)(row - (int64_t)b * p.h);
-  float rb[8];
+    const int b = (int)(row / H), y = (int)(row - (int64_t)b * H);
+    float rb[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) rb[j] = bs[j] + (p.rowbias ? p.rowbias[(int64_t)b * p.rowbias_ld + n0 + j] : 0.f);
-  const float* in = (const float*)p.a[0] + (int64_t)b * p.h * p.w * ld;
-  for (int x = lane; x < p.w; x += lanes) {
-    float v[9];
+    for (int j = 0; j < 8; ++j) rb[j] = bs[j] + (p.rowbias ? p.rowbias[(int64_t)b * p.rowbias_ld + n0 + j] : 0.f);
+    const float* in = (const float*)p.a[0] + (int64_t)b * H * W * ld;
+    const float* r0 = y > 0 ? in + (int64_t)(y - 1) * W * ld : nullptr;
+    const float* r1 = in + (int64_t)y * W * ld;
+    const float* r2 = y + 1 < H ? in + (int64_t)(y + 1) * W * ld : nullptr;
+    for (int x = lane * 2; x < W; x += lanes * 2) {
+      float v[3][4];                               // rows y-1..y+1, columns x-1..x+2
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
-      v[t] = (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) ? __ldg(in + ((int64_t)iy * p.w + ix) * ld) : 0.f;
+      for (int c = 0; c < 4; ++c) {
+        const int ix = x - 1 + c;
+        const bool okx = ix >= 0 && ix < W;
+        v[0][c] = (okx && r0) ? __ldg(r0 + (int64_t)ix * ld) : 0.f;
+        v[1][c] = okx ? __ldg(r1 + (int64_t)ix * ld) : 0.f;
+        v[2][c] = (okx && r2) ? __ldg(r2 + (int64_t)ix * ld) : 0.f;
+      }
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        if (x + px >= W) break;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = rb[j];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) a = fmaf(v[t / 3][t % 3 + px], w[t][j], a);
+          acc[j] = apply_act(a * p.alpha, p.act);
+        }
+        const int64_t pix = row * W + x + px;
+        TO* op = (TO*)p.out + pix * p.out_ld + p.out_coff + n0;
+        if constexpr (sizeof(TO) == 2) {
+          store_vec<TO>(op, acc);
+        } else {
+          float lo[4] = {acc[0], acc[1], acc[2], acc[3]}, hi[4] = {acc[4], acc[5], acc[6], acc[7]};
+          store_vec<float>((float*)op, lo);
+          store_vec<float>((float*)op + 4, hi);
+        }
+      }
     }
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = 0.f;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(v[t], w[t][j], a);
-      acc[j] = apply_act((a + rb[j]) * p.alpha, p.act);
-    }
-    const int64_t pix = row * p.w + x;
-    TO* op = (TO*)p.out + pix * p.out_ld + p.out_coff + n0;
-    if constexpr (sizeof(TO) == 2) {
-      store_vec<TO>(op, acc);
-    } else {
-      float lo[4] = {acc[0], acc[1], acc[2], acc[3]}, hi[4] = {acc[4], acc[5], acc[6], acc[7]};
-      store_vec<float>((float*)op, lo);
-      store_vec<float>((float*)op + 4, hi);
-    }
-  }
   }
 }
 

@@ -20,7 +20,7 @@ static inline int gn_ppb(int64_t hw, int C) {
   return (int)(a < b ? a : b);
 }
 template <typename T>
-__global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const T* __restrict__ x1, int c1, int ld1,
+__global__ void __launch_bounds__(256, 3) gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const T* __restrict__ x1, int c1, int ld1,
                                 int64_t hw, int groups, double* __restrict__ stats, int st_ld, int st_off,
                                 double* __restrict__ partial, unsigned int* __restrict__ tickets, int GN_PPB) {
   constexpr int V = 16 / sizeof(T);
@@ -43,22 +43,24 @@ __global__ void gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const
   for (int i = 0; i < V; ++i) { sum[i] = 0.f; sq[i] = 0.f; }
   const int64_t p0 = (int64_t)blockIdx.x * GN_PPB;
   int64_t p1 = p0 + GN_PPB; if (p1 > hw) p1 = hw;
-  constexpr int U = 4;
-  for (int64_t p = p0 + lane; p < p1; p += (int64_t)lanes * U) {
-    float v[U][V];
+  constexpr int U = 8;                        // 8 x 16 B in flight per thread
+  int64_t p = p0 + lane;
+  for (; p + (int64_t)(U - 1) * lanes < p1; p += (int64_t)lanes * U) {       // full groups: no predication
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) raw[u] = *reinterpret_cast<const uint4*>(base + (p + (int64_t)u * lanes) * ld + cc);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t pp = p + (int64_t)u * lanes;
-      if (pp < p1) load_vec<T>(base + pp * ld + cc, v[u]);
-    }
+      const T* e = reinterpret_cast<const T*>(&raw[u]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t pp = p + (int64_t)u * lanes;
-      if (pp < p1) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) { sum[i] += v[u][i]; sq[i] = fmaf(v[u][i], v[u][i], sq[i]); }
-      }
+      for (int i = 0; i < V; ++i) { const float f = Cvt<T>::to_f(e[i]); sum[i] += f; sq[i] = fmaf(f, f, sq[i]); }
     }
+  }
+  for (; p < p1; p += lanes) {                                               // tail
+    float v[V];
+    load_vec<T>(base + p * ld + cc, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { sum[i] += v[i]; sq[i] = fmaf(v[i], v[i], sq[i]); }
   }
 #pragma unroll
   for (int i = 0; i < V; ++i) {

@@ -16,7 +16,10 @@ SQRT2_INV = 1.0 / math.sqrt(2.0)
 import os as _os
 _ENV_FLAGS = 2 if _os.environ.get('MUDIFF_HALO', '1') == '0' else 0     # debug knob: forbid halo staging
 
-FUSED_STATS_MIN_N = int(_os.environ.get('MUDIFF_FUSED_STATS_MIN_N', '128'))
+# Fused epilogue statistics (conv_tc butterfly reduction) are implemented and tested, but since the MMA issue
+# loop got fast they cost more than the stand-alone HBM-bound statistics pass for every N <= 256 (measured,
+# tools/conv_bench.py): off by default, `fused_stats=True` / MUDIFF_FUSED_STATS_MIN_N turn them on.
+FUSED_STATS_MIN_N = int(_os.environ.get('MUDIFF_FUSED_STATS_MIN_N', '100000'))
 
 # Optional per-launch profiler (bench.py): callable(kind, flops, bytes) -> context manager or None.
 _PROFILER = None
@@ -212,7 +215,7 @@ def tc_eligible(segs, n, stride, dtype) -> bool:
 
 def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta=0.0, act=L.ACT_NONE,
          out=None, out_coff=0, out_dtype=None, stride=1, pad=1, w_bstride=0, w_ld=0, a_batched=True,
-         batch=None, flags=0, force=None, want_stats=False, stats_out=None, dec2=False):
+         batch=None, flags=0, force=None, want_stats=False, stats_out=None, dec2=False, fused_stats=None):
     """Implicit-GEMM convolution.  segs = [(tensor NCHW-logical/channels-last, taps)], wt packed K-major.
     Chooses the tcgen05 kernel when eligible (bf16, Cin % 64 == 0, N % 32 == 0, stride 1), otherwise the
     CUDA-core kernel.  `force` in {None,'tc','simt'}."""
@@ -276,7 +279,8 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
     tpi = 0
     # fused epilogue statistics pay off only when the MMA phase of a tile is long enough to hide the
     # butterfly reduction (N >= 128); N = 64 outputs get a stand-alone statistics pass (HBM-bound, cheaper)
-    if want_stats and use_tc and FUSED_STATS_MIN_N <= n <= 256:
+    use_fused = (n >= FUSED_STATS_MIN_N) if fused_stats is None else bool(fused_stats)
+    if want_stats and use_tc and use_fused and n <= 256:
         q = (C.c_int32 * 10)()
         L.check(L.lib().mudiff_conv_tc_query(C.byref(d), q), 'conv_tc_query')
         tpi = q[2]

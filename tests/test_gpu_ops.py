@@ -222,7 +222,8 @@ def test_conv_tc_vs_fp32_reference(M, name):
         ref = torch.sigmoid(ref)
         kw['act'] = 2
     wt = torch.cat(ws, dim=1).contiguous()
-    out = ops.conv(segs, wt, N, out_dtype=torch.float32, flags=c['flags'], force='tc', want_stats=N <= 256, **kw)
+    out = ops.conv(segs, wt, N, out_dtype=torch.float32, flags=c['flags'], force='tc', want_stats=N <= 256,
+                   fused_stats=True, **kw)
     scale = max(ref.abs().max().item(), 1.0)
     tol = 5e-3 if c.get('act') == 2 else 2e-3          # sigmoid epilogue uses tanh.approx
     assert (out.cpu() - ref).abs().max().item() <= tol * scale
@@ -244,7 +245,7 @@ def test_conv_tc_decimated_equals_stride2_valid(M):
     bias = torch.randn(128)
     ref = F.conv2d(x.float(), w.float(), bias, stride=2, padding=0)
     y = ops.conv([(ops.as_nhwc(x.cuda()), 9)], ops.pack_conv_weight(w.cuda(), (64,), torch.bfloat16), 128,
-                 bias=bias.cuda(), pad=1, dec2=True, out_dtype=torch.float32, want_stats=True)
+                 bias=bias.cuda(), pad=1, dec2=True, out_dtype=torch.float32, want_stats=True, fused_stats=True)
     assert tuple(y.shape) == tuple(ref.shape) == (3, 128, 16, 16)
     assert (y.cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
     cs = ops.get_chstats(y).cpu()
