@@ -262,7 +262,11 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
           float a = rb[j];
 #pragma unroll
           for (int t = 0; t < 9; ++t) a = fmaf(v[t / 3][t % 3 + px], w[t][j], a);
-          acc[j] = apply_act(a * p.alpha, p.act);
+          acc[j] = a * p.alpha;
+        }
+        if (p.act != MUDIFF_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], p.act);
         }
         const int64_t pix = row * W + x + px;
         TO* op = (TO*)p.out + pix * p.out_ld + p.out_coff + n0;
