@@ -169,6 +169,7 @@ int mudiff_conv_tc_query(const mudiff_conv_desc* d, int32_t* out);
 /* Debug: out[0..7] = (timed_out, block, warp, lane, barrier smem address, parity, grid, 0) of the last mbarrier
  * wait that hit its 4e9-cycle bound inside mudiff_conv_tc (kept in mapped host memory). */
 int mudiff_debug_last_timeout(int32_t* out);
+int mudiff_debug_dump(int32_t* out, int n);   /* header + the stuck CTA's barrier block / per-warp progress records */
 int mudiff_debug_selftest(void);   /* 1 if the mapped-host debug channel works */
 /* CUDA-core implicit GEMM (fp32 or bf16 storage, fp32 math): any shape, stride 1/2.
  * This is the fp32-parity path and the path for Cin=1 / Cout=1 / strided convs. */

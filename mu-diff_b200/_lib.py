@@ -54,6 +54,7 @@ PROTOTYPES = {
     'mudiff_conv_tc': [C.POINTER(ConvDesc), _P],
     'mudiff_conv_tc_query': [C.POINTER(ConvDesc), C.POINTER(C.c_int32)],
     'mudiff_debug_last_timeout': [C.POINTER(C.c_int32)],
+    'mudiff_debug_dump': [C.POINTER(C.c_int32), _I],
     'mudiff_debug_selftest': [],
     'mudiff_conv_simt': [C.POINTER(ConvDesc), _I, _P],
     'mudiff_softmax_rows': [_P, _P, _I, _L, _I, _F, _P],
@@ -103,7 +104,7 @@ class _Proxy:
             else:
                 with prof(name):
                     rc = fn(*args)
-            if do_sync and name not in ('mudiff_debug_last_timeout', 'mudiff_debug_selftest', 'mudiff_conv_tc_query'):
+            if do_sync and name not in ('mudiff_debug_last_timeout', 'mudiff_debug_dump', 'mudiff_debug_selftest', 'mudiff_conv_tc_query'):
                 counter[0] += 1
                 try:
                     torch.cuda.synchronize()

@@ -38,12 +38,13 @@ struct TcParams {
   int seg_cblk[3], seg_taps[3], seg_halo[3], seg_koff[3], seg_c[3];
   int a_batched, w_batched;
   uint32_t a_slot_bytes, b_sub_bytes, off_b, off_stats, off_bar;
-  int a_slots, b_slots, stationary, b_total_subs;
+  int a_slots, a_ring, b_slots, stationary, b_total_subs;   // a_slots = MT * a_ring
   uint32_t idesc;
   int acc_stride, acc_stages, tmem_cols;
   int base_off_variant;
   int round_robin;                            // debug: interleaved instead of contiguous unit assignment
   int dbg_dry, dbg_noepi, dbg_nostore, dbg_noldtm;
+  int dbg_skew;                               // adversarial schedules: bit0 delay MMA warp 2, bit1 MMA warp 3, bit2 epilogue, bit3 A producer
   int dec2, Ho, Wo;                           // stride-2 VALID conv as a decimated 'same' conv: keep odd (y, x) only                     // debug: no operand traffic / no epilogue work (timing only)
   // epilogue
   const float* bias; const float* rowbias; int rowbias_ld;
@@ -77,23 +78,49 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a launch error, never as a hung GPU.  Before trapping,
-// the waiter records who it was in a mapped host buffer (readable after the context died).
-__device__ int* g_dbg_host = nullptr;         // device pointer of a pinned, mapped host int[16]
-__device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+// the waiter copies the CTA's whole 1 KB barrier block (all mbarrier words + one progress record per
+// warp) into a mapped host buffer (readable after the context died): tools/decode_timeout.py.
+__device__ int* g_dbg_host = nullptr;         // device pointer of a pinned, mapped host int[1024]
+__device__ int g_dbg_lock = 0;                // first timed-out waiter writes the record
+constexpr int kDbgRecOff = 640;               // byte offset of the per-warp records inside the barrier block
+__device__ int g_dbg_done = 0;
+__device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity, const uint8_t* bar_block) {
   int* d = g_dbg_host;
   if (d) {
-    d[1] = (int)blockIdx.x; d[2] = (int)(threadIdx.x >> 5); d[3] = (int)(threadIdx.x & 31);
-    d[4] = (int)smem_u32(bar); d[5] = (int)parity; d[6] = (int)gridDim.x;
-    d[0] = 1;
-    __threadfence_system();
+    if (atomicCAS(&g_dbg_lock, 0, 1) == 0) {
+      d[1] = (int)blockIdx.x; d[2] = (int)(threadIdx.x >> 5); d[3] = (int)(threadIdx.x & 31);
+      d[4] = (int)smem_u32(bar); d[5] = (int)parity; d[6] = (int)gridDim.x; d[7] = (int)smem_u32(bar_block);
+      const int* src = reinterpret_cast<const int*>(bar_block);
+      for (int i = 0; i < 256; ++i) d[16 + i] = src[i];
+      __threadfence_system();
+      d[0] = 1;
+      __threadfence_system();
+      atomicExch(&g_dbg_done, 1);
+    } else {                                   // let the first waiter finish its record before the trap kills the grid
+      const long long t0 = clock64();
+      while (atomicAdd(&g_dbg_done, 0) == 0 && clock64() - t0 < 200000000LL) {}
+    }
   }
   __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// rec = this warp's int[4] progress record {barrier byte offset in the block, parity, tag, waiting?}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const uint8_t* bar_block, int tag) {
   if (mbar_try_wait(bar, parity)) return;
+  int* rec = (int*)(bar_block + kDbgRecOff) + (threadIdx.x >> 5) * 4;
+  if ((threadIdx.x & 31) == 0) {
+    rec[0] = (int)(smem_u32(bar) - smem_u32(bar_block)); rec[1] = (int)parity; rec[2] = tag; rec[3] = 1;
+  }
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity);
+    if (clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity, bar_block);
+  }
+  if ((threadIdx.x & 31) == 0) rec[3] = 0;
+}
+// progress mark outside of mbarrier waits (named barriers, TMEM loads): code < 0
+__device__ __forceinline__ void dbg_mark(const uint8_t* bar_block, int code, int tag) {
+  if ((threadIdx.x & 31) == 0) {
+    int* rec = (int*)(bar_block + kDbgRecOff) + (threadIdx.x >> 5) * 4;
+    rec[0] = code; rec[2] = tag; rec[3] = 2;
   }
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -200,6 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint8_t* bar_block = smem + p.off_bar;
   uint64_t* a_full = (uint64_t*)(smem + p.off_bar);
   uint64_t* a_empty = a_full + kMaxSlots;
   uint64_t* b_full = a_empty + kMaxSlots;
@@ -215,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.MT); }     // one arrival per issuing warp
+    for (int i = 0; i < 32; ++i) ((int*)(bar_block + kDbgRecOff))[i] = 0;
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], p.MT); mbar_init(&tempty_bar[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -240,7 +269,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (warp == 0) {
     // =========================== A producer ===========================
     if (lane == 0 && !p.dbg_dry) {
-      uint32_t a_item = 0;
+      // One A ring PER ISSUING WARP (tile m of every group goes to ring m, `a_ring` slots each): every ring has
+      // exactly one in-order consumer.  A single ring shared by the two MMA warps let slots alternate between
+      // them whenever the ring size was odd; the faster warp could then be two phases ahead on a slot and
+      // its parity wait passed on the previous phase (ABA) -> stale operands / deadlock (seen on B200).
+      uint32_t a_cnt0 = 0, a_cnt1 = 0;
+      const uint32_t ra = (uint32_t)p.a_ring;
       for (long long u = u_begin; u < u_end; u += u_step) {
         const Unit un = decode_unit(p, u);
         const int ab = p.a_batched ? un.b : 0;
@@ -250,9 +284,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int r = un.r0 + m;
             const int ty = r / p.tiles_x;
             const int y0 = ty * p.tile_h, x0 = (r - ty * p.tiles_x) * p.tile_w;
-            const uint32_t slot = a_item % (uint32_t)p.a_slots;
-            const uint32_t par = ((a_item / (uint32_t)p.a_slots) & 1u) ^ 1u;
-            mbar_wait(&a_empty[slot], par);
+            if (p.dbg_skew & 8) __nanosleep(1500);
+            const uint32_t k = m == 0 ? a_cnt0 : a_cnt1;
+            const uint32_t slot = (uint32_t)m * ra + k % ra;
+            const uint32_t par = ((k / ra) & 1u) ^ 1u;
+            mbar_wait(&a_empty[slot], par, bar_block, (int)k);
             uint8_t* sa = smem + (size_t)slot * p.a_slot_bytes;
             if (nb == 9) {
               mbar_expect_tx(&a_full[slot], (uint32_t)(p.tile_w + 2) * (p.tile_h + 2) * 128u);
@@ -263,7 +299,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               mbar_expect_tx(&a_full[slot], 128u * 128u);
               tma_load_4d(sa, mapA, &a_full[slot], cb * 64, x0 + dx, y0 + dy, ab);
             }
-            ++a_item;
+            if (m == 0) ++a_cnt0; else ++a_cnt1;
           }
         });
       }
@@ -285,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               const int tp = nb == 9 ? j : tap;
               const uint32_t slot = b_item % (uint32_t)p.b_slots;
               const uint32_t par = ((b_item / (uint32_t)p.b_slots) & 1u) ^ 1u;
-              mbar_wait(&b_empty[slot], par);
+              mbar_wait(&b_empty[slot], par, bar_block, (int)b_item);
               mbar_expect_tx(&b_full[slot], p.b_sub_bytes);
               tma_load_3d(smem + p.off_b + (size_t)slot * p.b_sub_bytes, &mapW, &b_full[slot],
                           p.seg_koff[s] + tp * p.seg_c[s] + cb * 64, un.n0, wb);
@@ -315,19 +351,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t a_lo_base = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t a_step = p.a_slot_bytes >> 4;
     const bool dry = p.dbg_dry != 0;
-    if (p.stationary && !dry) { mbar_wait(w_full, 0); tc_fence_after(); }
+    if (p.stationary && !dry) { mbar_wait(w_full, 0, bar_block, -1); tc_fence_after(); }
     for (long long u = u_begin; u < u_end; u += u_step) {
       const Unit un = decode_unit(p, u);
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1, bar_block, (int)(u - u_begin));
       tc_fence_after();
       uint32_t accum = 0;                                  // 0 only for the first MMA of the accumulator
       const uint32_t d_mine = tmem_base + (uint32_t)((acc * p.MT + me) * p.acc_stride);
       const bool active = me < un.count;                   // partial last group of an image: tile 1 may not exist
       for_each_group(p, [&](int s, int cb, int tap, int nb) {
-        // my A tile of this group
-        uint32_t sl = a_slot + (uint32_t)me, ph = a_phase;
-        if (sl >= (uint32_t)p.a_slots) { sl -= (uint32_t)p.a_slots; ph ^= 1u; }
-        if (active && !dry) mbar_wait(&a_full[sl], ph);
+        if (p.dbg_skew & (1 << me)) __nanosleep(2000);
+        // my A tile of this group: next slot of MY ring (ring `me`, in order)
+        const uint32_t sl = (uint32_t)me * (uint32_t)p.a_ring + a_slot, ph = a_phase;
+        if (active && !dry) mbar_wait(&a_full[sl], ph, bar_block, (int)(u - u_begin));
         tc_fence_after();
         const uint32_t alo = a_lo_base + sl * a_step;
         const uint32_t hi_a = nb == 9 ? hi_a_halo : hi_b;
@@ -340,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (p.stationary) {
               blo = b_lo_base + (uint32_t)(kbase + j * kstep) * b_step;
             } else {
-              if (!dry) mbar_wait(&b_full[b_slot], b_phase);
+              if (!dry) mbar_wait(&b_full[b_slot], b_phase, bar_block, (int)(u - u_begin));
               tc_fence_after();
               blo = b_lo_base + b_slot * b_step;
             }
@@ -360,9 +396,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             accum = 1u;
           }
         }
-        if (leader && active) tc_commit(&a_empty[sl]);              // my A tile is free once its last tap retires
-        a_slot += (uint32_t)un.count;
-        if (a_slot >= (uint32_t)p.a_slots) { a_slot -= (uint32_t)p.a_slots; a_phase ^= 1u; }
+        if (active) {
+          if (leader) tc_commit(&a_empty[sl]);                      // my A tile is free once its last tap retires
+          if (++a_slot == (uint32_t)p.a_ring) { a_slot = 0; a_phase ^= 1u; }
+        }
       });
       if (leader) tc_commit(&tfull_bar[acc]);                // my accumulator is complete -> epilogue
       if (p.acc_stages == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
@@ -382,6 +419,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const Unit un = decode_unit(p, u);
       if ((p.bias || p.rowbias) && (un.b != bias_b || un.n0 != bias_n0)) {
         // stage bias[n] + rowbias[b][n] once per (image, N tile); all 128 epilogue threads take part
+        dbg_mark(bar_block, -2, (int)(u - u_begin));
         asm volatile("bar.sync 2, 128;" ::: "memory");
         for (int col = et; col < p.n_tile; col += 128) {
           float bv = p.bias ? __ldg(p.bias + un.n0 + col) : 0.f;
@@ -391,8 +429,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         asm volatile("bar.sync 2, 128;" ::: "memory");
         bias_b = un.b; bias_n0 = un.n0;
       }
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      if (p.dbg_skew & 4) __nanosleep(20000);
+      mbar_wait(&tfull_bar[acc], acc_phase, bar_block, (int)(u - u_begin));
       tc_fence_after();
+      dbg_mark(bar_block, -3, (int)(u - u_begin));
       for (int m = 0; m < (p.dbg_noepi ? 0 : un.count); ++m) {
         const int r = un.r0 + m;
         const int tyt = r / p.tiles_x;
@@ -507,6 +547,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
+      dbg_mark(bar_block, -4, (int)(u - u_begin));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -656,6 +697,7 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
     p.b_total_subs = ktot / 64;
     int as = (int)((avail - b_total) / p.a_slot_bytes);
     p.a_slots = as > 8 ? 8 : as;
+    p.a_slots -= p.a_slots % MT;
     p.b_slots = 0;
     p.off_b = (uint32_t)p.a_slots * p.a_slot_bytes;
     p.off_stats = p.off_b + b_total;
@@ -669,12 +711,15 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
     if (bs > 12) {                      // spend the surplus on a deeper A ring
       int extra = (int)(((uint32_t)(bs - 12) * p.b_sub_bytes) / p.a_slot_bytes);
       p.a_slots += extra; if (p.a_slots > 8) p.a_slots = 8;
+      p.a_slots -= p.a_slots % MT;
       bs = 12;
     }
     p.b_slots = bs;
     p.off_b = (uint32_t)p.a_slots * p.a_slot_bytes;
     p.off_stats = p.off_b + (uint32_t)bs * p.b_sub_bytes;
   }
+  p.a_ring = p.a_slots / MT;
+  if (p.a_ring < 1 || p.a_ring * MT != p.a_slots) return MUDIFF_EUNSUPPORTED;
   p.off_bar = p.off_stats + ((stats_bytes + 1023u) & ~1023u);
   if (p.off_bar + bar_bytes + 1024u > kSmemMax) return MUDIFF_EUNSUPPORTED;
   // UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, N = n_tile, M = 128
@@ -685,6 +730,7 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   p.dbg_noepi = (d->flags & 128) ? 1 : 0;
   p.dbg_nostore = (d->flags & 2048) ? 1 : 0;
   p.dbg_noldtm = (d->flags & 4096) ? 1 : 0;
+  p.dbg_skew = (d->flags >> 16) & 15;
   p.dec2 = (d->flags & 32768) ? 1 : 0;
   p.Ho = p.dec2 ? (d->h - 1) / 2 : d->h;
   p.Wo = p.dec2 ? (d->w - 1) / 2 : d->w;
@@ -697,15 +743,15 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
 
 }  // namespace
 
-__global__ void dbg_selftest_kernel() { if (g_dbg_host) { g_dbg_host[7] = 12345; __threadfence_system(); } }
+__global__ void dbg_selftest_kernel() { if (g_dbg_host) { g_dbg_host[8] = 12345; __threadfence_system(); } }
 static int* g_dbg_host_ptr = nullptr;
 static void ensure_dbg() {
   static bool done = false;
   if (done) return;
   done = true;
   int* h = nullptr;
-  if (cudaHostAlloc((void**)&h, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
-  memset(h, 0, 64);
+  if (cudaHostAlloc((void**)&h, 4096 + 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
+  memset(h, 0, 4096 + 64);
   int* dptr = nullptr;
   if (cudaHostGetDevicePointer((void**)&dptr, h, 0) != cudaSuccess) { cudaGetLastError(); return; }
   if (cudaMemcpyToSymbol(g_dbg_host, &dptr, sizeof(dptr)) != cudaSuccess) { cudaGetLastError(); return; }
@@ -719,12 +765,19 @@ extern "C" int mudiff_debug_selftest(void) {
   if (!g_dbg_host_ptr) return -1;
   dbg_selftest_kernel<<<1, 1>>>();
   if (cudaDeviceSynchronize() != cudaSuccess) return -2;
-  return ((volatile int*)g_dbg_host_ptr)[7] == 12345 ? 1 : 0;
+  return ((volatile int*)g_dbg_host_ptr)[8] == 12345 ? 1 : 0;
 }
 
 extern "C" int mudiff_debug_last_timeout(int32_t* out) {
   if (!g_dbg_host_ptr) { for (int i = 0; i < 8; ++i) out[i] = 0; return 0; }
   for (int i = 0; i < 8; ++i) out[i] = ((volatile int*)g_dbg_host_ptr)[i];
+  return 0;
+}
+
+// Full record of the last timeout: out[0..15] header as above (out[7] = shared address of the barrier block),
+// out[16..271] = the CTA's 1 KB barrier block (mbarrier words, then per-warp progress records at byte 640).
+extern "C" int mudiff_debug_dump(int32_t* out, int n) {
+  for (int i = 0; i < n; ++i) out[i] = (g_dbg_host_ptr && i < 1024 + 16) ? ((volatile int*)g_dbg_host_ptr)[i] : 0;
   return 0;
 }
 

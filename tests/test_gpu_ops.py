@@ -235,6 +235,44 @@ def test_conv_tc_vs_fp32_reference(M, name):
         np.testing.assert_allclose(cs[..., 1].numpy(), (o64 ** 2).sum(dim=(2, 3)).numpy(), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize('skew', [1, 2, 4, 8, 3, 6])
+@pytest.mark.parametrize('shape', ['shortcut_k832', 'stream_n128', 'gemm_k256'])
+def test_conv_tc_adversarial_schedules(M, skew, shape):
+    """Protocol regression test: one role of the warp-specialised kernel is slowed down on purpose (MMA warp of
+    tile 0 / tile 1, epilogue, A producer) so that the others run as far ahead as the rings allow.  Results
+    must not change.  'shortcut_k832' is the launch (3x3 over 64 ch + fused 1x1 shortcut over 256 ch, N = 64)
+    whose odd-sized shared A ring let one MMA warp get two mbarrier phases ahead of the other (parity ABA)."""
+    from mudiff_b200 import ops
+    torch.manual_seed(5)
+    if shape == 'shortcut_k832':
+        B, H, W, C, taps, N = 8, 128, 128, [64, 256], [9, 1], 64
+    elif shape == 'stream_n128':
+        B, H, W, C, taps, N = 8, 128, 128, [128], [9], 128
+    else:
+        B, H, W, C, taps, N = 4, 1, 8192, [256], [1], 1024
+    segs, ws = [], []
+    for ci, tp in zip(C, taps):
+        x = torch.randn(B, ci, H, W, device='cuda').to(torch.bfloat16)
+        k = 3 if tp == 9 else 1
+        w = (torch.randn(N, ci, k, k, device='cuda') / (ci * tp) ** 0.5).to(torch.bfloat16)
+        segs.append((ops.as_nhwc(x), tp))
+        ws.append(ops.pack_conv_weight(w, (ci,), torch.bfloat16))
+    wt = torch.cat(ws, dim=1).contiguous()
+    bias = torch.randn(N, device='cuda')
+    ref = ops.conv(segs, wt, N, bias=bias, force='tc')
+    torch.cuda.synchronize()
+    for _ in range(3):
+        out = ops.conv(segs, wt, N, bias=bias, force='tc', flags=skew << 16)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)                     # same kernel, same summation order: bit-exact
+    # and the unskewed result is right (fp32 reference on the bf16-exact operands)
+    if shape != 'gemm_k256':
+        r32 = sum(F.conv2d(s.float(), wq.float().reshape(N, -1, ci).permute(0, 2, 1).reshape(N, ci, *( (3, 3) if tp == 9 else (1, 1))),
+                           padding=1 if tp == 9 else 0)
+                  for (s, tp), wq, ci in zip(segs, ws, C)) + bias[None, :, None, None]
+        assert (ref.float() - r32).abs().max().item() <= 2e-2 * max(r32.abs().max().item(), 1.0)
+
+
 def test_conv_tc_decimated_equals_stride2_valid(M):
     """conv_downsample_2d's stride-2 VALID 3x3 conv (up_or_down_sampling.py:183) on the tensor cores:
     odd outputs of the pad-1 'same' conv."""
