@@ -166,6 +166,11 @@ int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream);
 /* Planning only: out[0..9] = tile_h, tile_w, tiles_per_image, n_tile, tiles_per_unit, stationary_weights,
  * a_slots, b_slots, accumulator_stages, halo(seg0).  Callers size `stats` with out[2]. */
 int mudiff_conv_tc_query(const mudiff_conv_desc* d, int32_t* out);
+
+/* Fused attention of AttnBlockpp (backbones/layerspp.py:118-122: einsum -> softmax -> einsum) in one tcgen05 kernel:
+ * out[b] = softmax(Q[b] K[b]^T * scale) V[b].  qk [B, L, 2C] bf16 (q | k per token), vt = V^T [B, C, L] bf16,
+ * out [B, L, C] bf16.  C == 256, L % 128 == 0, else MUDIFF_EUNSUPPORTED (callers use the unfused kernels). */
+int mudiff_attention_tc(const void* qk, const void* vt, void* out, int batch, int L, int C, float scale, void* stream);
 /* Debug: out[0..7] = (timed_out, block, warp, lane, barrier smem address, parity, grid, 0) of the last mbarrier
  * wait that hit its 4e9-cycle bound inside mudiff_conv_tc (kept in mapped host memory). */
 int mudiff_debug_last_timeout(int32_t* out);

@@ -53,6 +53,7 @@ PROTOTYPES = {
     'mudiff_zero': [_P, _L, _P],
     'mudiff_conv_tc': [C.POINTER(ConvDesc), _P],
     'mudiff_conv_tc_query': [C.POINTER(ConvDesc), C.POINTER(C.c_int32)],
+    'mudiff_attention_tc': [_P, _P, _P, _I, _I, _I, _F, _P],
     'mudiff_debug_last_timeout': [C.POINTER(C.c_int32)],
     'mudiff_debug_dump': [C.POINTER(C.c_int32), _I],
     'mudiff_debug_selftest': [],

@@ -283,58 +283,112 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
 }
 
 // ---------------------------------------------------------------------------------
-// head kernel: N == 1, 3x3 pad 1, stride 1, single segment, Cin % 64 == 0 (the nf->1 output conv,
-// with the tanh of ncsnpp_generator_adagn_feat.py:445 in the epilogue).  HBM-read bound.
-// 8 lanes per pixel, each lane reads one 16-byte channel vector per tap (coalesced 128 B per pixel-tap),
-// weights of the lane's channels in registers, 3 shuffles to reduce.  One block per output row.
+// head kernel: N == 1, 3x3 pad 1, stride 1, single segment, Cin % 64 == 0 (the nf->1 output conv, with the
+// tanh of ncsnpp_generator_adagn_feat.py:445 in the epilogue).  HBM-read bound: every input pixel is read from
+// global memory ONCE per strip.  A warp owns 30 output columns x HEAD_YR rows: lane l holds input column
+// x0 - 1 + l, walks down the rows, and turns each loaded pixel into the nine per-tap dot products over its
+// channels; vertical taps roll through registers, horizontal taps are exchanged with the neighbour lanes by
+// shuffle (lanes 0 and 31 are halo columns).  Rows are fetched with fully coalesced 16-byte loads (one row
+// ahead, in registers) and re-distributed pixel-per-lane through a padded per-warp shared-memory tile.
 // ---------------------------------------------------------------------------------
-#define HEAD_ROWS 4
+#define HEAD_YR 32
+#define HEAD_COLS 30
 template <typename TA, typename TO>
-__global__ void __launch_bounds__(256) conv_head_kernel(SimtP p) {
-  constexpr int V = 16 / sizeof(TA);          // 8 (bf16) or 4 (fp32) channels per load
-  constexpr int LPP = 64 / V;                 // lanes per pixel for one 64-channel block: 8 or 16
-  const int sub = threadIdx.x % LPP;
-  const int lane = threadIdx.x / LPP, lanes = blockDim.x / LPP;
+__global__ void __launch_bounds__(256, 2) conv_head_kernel(SimtP p, int xchunks, int ystrips) {
+  constexpr int V = 16 / sizeof(TA);          // 8 (bf16) or 4 (fp32) channels per 16-byte load
+  constexpr int PB = 64 * sizeof(TA);         // bytes of one 64-channel block of a pixel: 128 / 256
+  constexpr int NV = PB / 16;                 // 16-byte vectors per pixel block: 8 / 16
+  constexpr int PITCH = PB + 16;              // padded pixel pitch -> conflict-free 16-byte accesses
+  extern __shared__ __align__(16) uint8_t head_smem[];
   const int C = p.a_c[0];
+  float* sw = reinterpret_cast<float*>(head_smem);                    // [9][C] fp32 weights
+  uint8_t* tile = head_smem + (size_t)9 * C * 4 + (threadIdx.x >> 5) * (32 * PITCH);
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[i] = Cvt<TA>::to_f(((const TA*)p.wt)[i]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t unit = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t units = (int64_t)p.batch * ystrips * xchunks;
+  if (unit >= units) return;
+  const int xc = (int)(unit % xchunks);
+  const int ys = (int)((unit / xchunks) % ystrips);
+  const int b = (int)(unit / ((int64_t)xchunks * ystrips));
+  const int x0 = xc * HEAD_COLS;                 // first output column of this warp
+  const int y0 = ys * HEAD_YR;
+  const int y1 = min(y0 + HEAD_YR, p.h);
   const int ld = p.a_ld[0];
-  const TA* wt = (const TA*)p.wt;
-  const bool one_block = C == 64;
-  float wreg[9][V];                           // weights of this lane's channels (first 64-channel block)
+  const TA* in = (const TA*)p.a[0] + (int64_t)b * p.h * p.w * ld;
+  const int nblk = C / 64;
+  const float bias = (p.bias ? p.bias[0] : 0.f) + (p.rowbias ? p.rowbias[(int64_t)b * p.rowbias_ld] : 0.f);
+  float r0[3] = {0.f, 0.f, 0.f}, r1[3] = {0.f, 0.f, 0.f};
+  // coalesced fetch of one 64-channel block of row yy: vector j of the 32-pixel segment, j = lane + 32 i
+  auto fetch = [&](int yy, int cb, uint4 (&regs)[NV]) {
 #pragma unroll
-  for (int t = 0; t < 9; ++t) load_vec<TA>(wt + t * C + sub * V, wreg[t]);
-  const int64_t rows = (int64_t)p.batch * p.h;
-  for (int64_t row = (int64_t)blockIdx.x * HEAD_ROWS; row < rows && row < (int64_t)(blockIdx.x + 1) * HEAD_ROWS; ++row) {
-    const int b = (int)(row / p.h), y = (int)(row - (int64_t)b * p.h);
-    const TA* in = (const TA*)p.a[0] + (int64_t)b * p.h * p.w * ld;
-    for (int x = lane; x < p.w; x += lanes) {
-      float acc = 0.f;
+    for (int i = 0; i < NV; ++i) {
+      const int j = lane + 32 * i;
+      const int px = j / NV, vv = j % NV;
+      const int x = x0 - 1 + px;
+      regs[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (yy >= 0 && yy < p.h && x >= 0 && x < p.w)
+        regs[i] = *reinterpret_cast<const uint4*>(in + ((int64_t)yy * p.w + x) * ld + cb * 64 + vv * V);
+    }
+  };
+  uint4 nxt[NV];
+  fetch(y0 - 1, 0, nxt);
+  for (int yy = y0 - 1; yy <= y1; ++yy) {
+    float P[9];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
-        if (iy < 0 || iy >= p.h || ix < 0 || ix >= p.w) continue;
-        float v[V];
-        load_vec<TA>(in + ((int64_t)iy * p.w + ix) * ld + sub * V, v);
+    for (int t = 0; t < 9; ++t) P[t] = 0.f;
+    for (int cb = 0; cb < nblk; ++cb) {
+      __syncwarp();
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc = fmaf(v[k], wreg[t][k], acc);
+      for (int i = 0; i < NV; ++i) {
+        const int j = lane + 32 * i;
+        *reinterpret_cast<uint4*>(tile + (j / NV) * PITCH + (j % NV) * 16) = nxt[i];
       }
-      if (!one_block) {
-        for (int cb = 64; cb < C; cb += 64) {
-          const int c = cb + sub * V;
+      __syncwarp();
+      // prefetch the next block / row while this one is consumed
+      if (cb + 1 < nblk) fetch(yy, cb + 1, nxt);
+      else if (yy + 1 <= y1) fetch(yy + 1, 0, nxt);
+      const float* wb = sw + cb * 64;
+#pragma unroll 2
+      for (int vv = 0; vv < NV; ++vv) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(tile + lane * PITCH + vv * 16);
+        float v[V];
+        const TA* e = reinterpret_cast<const TA*>(&raw);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
-            if (iy < 0 || iy >= p.h || ix < 0 || ix >= p.w) continue;
-            float v[V], w[V];
-            load_vec<TA>(in + ((int64_t)iy * p.w + ix) * ld + c, v);
-            load_vec<TA>(wt + t * C + c, w);
+        for (int k = 0; k < V; ++k) v[k] = Cvt<TA>::to_f(e[k]);
 #pragma unroll
-            for (int k = 0; k < V; ++k) acc = fmaf(v[k], w[k], acc);
+        for (int t = 0; t < 9; ++t) {
+#pragma unroll
+          for (int k4 = 0; k4 < V; k4 += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wb + t * C + vv * V + k4);     // warp-uniform: broadcast
+            P[t] = fmaf(v[k4 + 0], w4.x, P[t]); P[t] = fmaf(v[k4 + 1], w4.y, P[t]);
+            P[t] = fmaf(v[k4 + 2], w4.z, P[t]); P[t] = fmaf(v[k4 + 3], w4.w, P[t]);
           }
         }
       }
+    }
+    // P[(dy+1)*3 + (dx+1)] is this pixel's contribution to out(yy - dy, x - dx)
+    float q[3];
 #pragma unroll
-      for (int o = LPP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (sub == 0) epilogue_store<TO>(p, b, row * p.w + x, 0, acc);
+    for (int d = 0; d < 3; ++d) {
+      q[d] = r1[d] + P[6 + d];                 // dy = +1 completes output row yy - 1
+      r1[d] = r0[d] + P[3 + d];                // dy =  0 -> output row yy
+      r0[d] = P[d];                            // dy = -1 -> output row yy + 1
+    }
+    // out(y, x) = q[dx=-1] of column x-1  +  q[dx=0] of column x  +  q[dx=+1] of column x+1
+    // tap index d = dx + 1 is the tap the INPUT column applies: input column x-1 feeds out(x) with dx = -1,
+    // i.e. the weight column index 0 ... careful: in(y+dy, x+dx) * w[dy][dx]; input column xi = x+dx -> dx = xi - x
+    const float from_left = __shfl_up_sync(0xffffffffu, q[0], 1);     // column x-1 holds dx = -1 -> d = 0
+    const float from_right = __shfl_down_sync(0xffffffffu, q[2], 1);  // column x+1 holds dx = +1 -> d = 2
+    const int y = yy - 1, x = x0 - 1 + lane;
+    if (y >= y0 && y < y1 && lane >= 1 && lane <= HEAD_COLS && x < p.w) {
+      const float acc = from_left + q[1] + from_right;
+      float v = (acc + bias) * p.alpha;
+      const int64_t pix = ((int64_t)b * p.h + y) * p.w + x;
+      if (p.residual) v = fmaf(p.beta, Cvt<TO>::to_f(((const TO*)p.residual)[pix * p.res_ld]), v);
+      v = apply_act(v, p.act);
+      ((TO*)p.out)[pix * p.out_ld + p.out_coff] = Cvt<TO>::from_f(v);
     }
   }
 }
@@ -354,10 +408,23 @@ int launch_simt(const SimtP& p, cudaStream_t st) {
       return mudiff_launch_status();
     }
   }
-  if (plain && s1 && p.n == 1 && p.a_c[0] % 64 == 0 && p.a_ld[0] % (16 / (int)sizeof(TA)) == 0 && rows < (1LL << 31) &&
-      ((uintptr_t)p.a[0] % 16 == 0) && ((uintptr_t)p.wt % 16 == 0)) {
-    conv_head_kernel<TA, TO><<<(unsigned)((rows + HEAD_ROWS - 1) / HEAD_ROWS), 256, 0, st>>>(p);
-    return mudiff_launch_status();
+  if (plain && s1 && p.n == 1 && p.a_c[0] % 64 == 0 && p.a_c[0] <= 512 && p.a_ld[0] % (16 / (int)sizeof(TA)) == 0 &&
+      ((uintptr_t)p.a[0] % 16 == 0)) {
+    const int xchunks = (p.w + HEAD_COLS - 1) / HEAD_COLS, ystrips = (p.h + HEAD_YR - 1) / HEAD_YR;
+    const int64_t units = (int64_t)p.batch * ystrips * xchunks;
+    const int64_t blocks = (units + 7) / 8;
+    if (blocks < (1LL << 31)) {
+      const size_t smem = (size_t)9 * p.a_c[0] * 4 + 8 * 32 * (64 * sizeof(TA) + 16);
+      static bool attr_done[2][2] = {};
+      bool& done = attr_done[sizeof(TA) == 4][sizeof(TO) == 4];
+      if (smem > 48 * 1024 && !done) {
+        if (cudaFuncSetAttribute(conv_head_kernel<TA, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+          return (int)cudaGetLastError();
+        done = true;
+      }
+      conv_head_kernel<TA, TO><<<(unsigned)blocks, 256, smem, st>>>(p, xchunks, ystrips);
+      return mudiff_launch_status();
+    }
   }
   if (plain && p.n <= 4 && (size_t)p.n * p.ktot * 4 <= 48 * 1024) {
     int64_t threads = (int64_t)p.batch * hw_o * 8;

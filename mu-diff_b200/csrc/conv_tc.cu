@@ -741,6 +741,8 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   return 0;
 }
 
+#include "attn_tc.cuh"
+
 }  // namespace
 
 __global__ void dbg_selftest_kernel() { if (g_dbg_host) { g_dbg_host[8] = 12345; __threadfence_system(); } }
@@ -788,6 +790,38 @@ extern "C" int mudiff_conv_tc_query(const mudiff_conv_desc* d, int32_t* out) {
   out[0] = p.tile_h; out[1] = p.tile_w; out[2] = p.tpi; out[3] = p.n_tile; out[4] = p.MT;
   out[5] = p.stationary; out[6] = p.a_slots; out[7] = p.b_slots; out[8] = p.acc_stages; out[9] = p.seg_halo[0];
   return 0;
+}
+
+// Fused attention O = softmax(Q K^T * scale) V (AttnBlockpp, backbones/layerspp.py:118-122), see attn_tc.cuh.
+extern "C" int mudiff_attention_tc(const void* qk, const void* vt, void* out, int batch, int L, int C, float scale,
+                                   void* stream) {
+  if (!qk || !vt || !out || batch <= 0 || L <= 0 || C <= 0) return MUDIFF_EINVAL;
+  if (C != 256 || L % 128) return MUDIFF_EUNSUPPORTED;
+  if (((uintptr_t)qk % 16) || ((uintptr_t)vt % 16) || ((uintptr_t)out % 16)) return MUDIFF_EUNSUPPORTED;
+  ensure_dbg();
+  CUtensorMap mqk, mv;
+  int rc = make_map_w(&mqk, qk, 2 * C, 2 * C, L, batch, (int64_t)L * 2 * C, 128);
+  if (rc) return rc;
+  rc = make_map_w(&mv, vt, L, L, C, batch, (int64_t)C * L, 256);
+  if (rc) return rc;
+  AttnP p;
+  p.batch = batch; p.L = L; p.C = C; p.qtiles = L / 128; p.nk = L / 128;
+  p.total_units = (long long)batch * p.qtiles;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = (__nv_bfloat16*)out;
+  p.idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+  static bool attr_set[16] = {};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev] = true;
+  }
+  const int grid = (int)(p.total_units < MUDIFF_NUM_SMS ? p.total_units : MUDIFF_NUM_SMS);
+  attn_tc_kernel<<<grid, 256, kAttnSmem, (cudaStream_t)stream>>>(mqk, mv, p);
+  return mudiff_launch_status();
 }
 
 extern "C" int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream) {

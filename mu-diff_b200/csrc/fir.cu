@@ -144,56 +144,117 @@ __global__ void fir_nchw_tiled_kernel(const T* __restrict__ in, T* __restrict__ 
   }
 }
 
-// Specialised NHWC kernel for the three modes the generators use (4x4 FIR): UP/DOWN in {1,2}.
-// One block per output row, a thread owns one 16-byte channel vector and walks the row; the
-// taps are compile-time unrolled (polyphase: up=2 touches 2x2 inputs, down=2 touches 4x4).
-template <typename T, int UP, int DOWN>
-__global__ void __launch_bounds__(256) fir4_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out,
-                                                        const float* __restrict__ kern, FirP p) {
-  constexpr int V = 16 / sizeof(T);
-  __shared__ float sk[16];
-  if (threadIdx.x < 16) {
-    int ky = threadIdx.x / 4, kx = threadIdx.x % 4;
-    sk[threadIdx.x] = kern[(3 - ky) * 4 + (3 - kx)];
+// Specialised NHWC kernels for the three modes the generators use (4x4 FIR, up_or_down_sampling.py:200-262):
+//   UP=2   (upsample_2d, pad (2,1))      DOWN=2 (downsample_2d, pad (1,1))      UP=DOWN=1 (pre-filter, pad (2,2))
+// A thread owns one 16-byte channel vector and computes a 2x2 block of outputs from the NRxNR input window that
+// block touches (3x3 / 6x6 / 5x5): 2.25 / 9 / 6.25 vector loads per output instead of 4 / 16 / 16, no
+// data-dependent branches (the polyphase structure is resolved at compile time), one window row (NR independent
+// 16-byte loads) in flight at a time, YB vertically adjacent blocks per thread so re-read rows hit L1.
+// Requires even pads for UP=2 (polyphase alignment); anything else goes to the generic kernels above.
+template <int UP, int DOWN> struct Fir4Geom {
+  static constexpr int NR = UP == 2 ? 3 : (DOWN == 2 ? 6 : 5);
+  // tap index of window row/col r for output offset d in {0,1}, or -1
+  static __host__ __device__ constexpr int tap(int d, int r) {
+    if (UP == 2) { const int t = r - d; return (t == 0 || t == 1) ? 2 * t + d : -1; }
+    if (DOWN == 2) { const int t = r - 2 * d; return (t >= 0 && t < 4) ? t : -1; }
+    { const int t = r - d; return (t >= 0 && t < 4) ? t : -1; }
   }
+};
+
+template <typename T, int UP, int DOWN, int YB>
+__global__ void __launch_bounds__(256) fir4_quad_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                        const float* __restrict__ kern, FirP p, int bxs, int bygs) {
+  using G = Fir4Geom<UP, DOWN>;
+  constexpr int V = 16 / sizeof(T);
+  constexpr int NR = G::NR;
+  __shared__ float sk[16];
+  if (threadIdx.x < 16) sk[threadIdx.x] = kern[15 - threadIdx.x];        // flipped: true convolution
   __syncthreads();
   float kf[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) kf[i] = sk[i];
   const int cv = p.minor / V;
-  const int row = blockIdx.x;                       // m * out_h + oy
-  const int m = row / p.out_h, oy = row - m * p.out_h;
-  const int c = (threadIdx.x % cv) * V;
-  const int lane = threadIdx.x / cv, lanes = blockDim.x / cv;
-  const T* inm = in + (int64_t)m * p.in_h * p.in_w * p.minor + c;
-  T* orow = out + ((int64_t)row * p.out_w) * p.minor + c;
-  const int by = oy * DOWN - p.py0;
-  for (int ox = lane; ox < p.out_w; ox += lanes) {
-    const int bx = ox * DOWN - p.px0;
-    float acc[V];
+  const int64_t total = p.major * bygs * (int64_t)bxs * cv;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cv) * V;
+  int64_t r_ = idx / cv;
+  const int bx = (int)(r_ % bxs); r_ /= bxs;
+  const int byg = (int)(r_ % bygs);
+  const int64_t m = r_ / bygs;
+  const T* inm = in + m * p.in_h * (int64_t)p.in_w * p.minor + c;
+  T* outm = out + m * p.out_h * (int64_t)p.out_w * p.minor + c;
+  const int ox0 = bx * 2;
+  // first input column of the window
+  const int ix0 = UP == 2 ? (ox0 - p.px0) / 2 : ox0 * DOWN - p.px0;      // UP=2: px0 even -> exact
+#pragma unroll 1
+  for (int yb = 0; yb < YB; ++yb) {
+    const int oy0 = (byg * YB + yb) * 2;
+    if (oy0 >= p.out_h) break;
+    const int iy0 = UP == 2 ? (oy0 - p.py0) / 2 : oy0 * DOWN - p.py0;
+    float acc[2][2][V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int ky = 0; ky < 4; ++ky) {
-      const int yy = by + ky;
-      if (UP == 2 && (yy & 1)) continue;
-      const int iy = UP == 2 ? yy >> 1 : yy;
-      if (yy < 0 || iy >= p.in_h) continue;
+      for (int b = 0; b < 2; ++b)
 #pragma unroll
-      for (int kx = 0; kx < 4; ++kx) {
-        const int xx = bx + kx;
-        if (UP == 2 && (xx & 1)) continue;
-        const int ix = UP == 2 ? xx >> 1 : xx;
-        if (xx < 0 || ix >= p.in_w) continue;
+        for (int i = 0; i < V; ++i) acc[a][b][i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int iy = iy0 + r;
+      const bool oky = iy >= 0 && iy < p.in_h;
+      uint4 raw[NR];
+#pragma unroll
+      for (int s2 = 0; s2 < NR; ++s2) {
+        const int ix = ix0 + s2;
+        raw[s2] = make_uint4(0u, 0u, 0u, 0u);
+        if (oky && ix >= 0 && ix < p.in_w) raw[s2] = *reinterpret_cast<const uint4*>(inm + ((int64_t)iy * p.in_w + ix) * p.minor);
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < NR; ++s2) {
         float v[V];
-        load_vec<T>(inm + ((int64_t)iy * p.in_w + ix) * p.minor, v);
-        const float w = kf[ky * 4 + kx];
+        const T* e = reinterpret_cast<const T*>(&raw[s2]);
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+        for (int i = 0; i < V; ++i) v[i] = Cvt<T>::to_f(e[i]);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const int ky = G::tap(dy, r);
+          if (ky < 0) continue;
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int kx = G::tap(dx, s2);
+            if (kx < 0) continue;
+            const float w = kf[ky * 4 + kx];
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[dy][dx][i] = fmaf(w, v[i], acc[dy][dx][i]);
+          }
+        }
       }
     }
-    store_vec<T>(orow + (int64_t)ox * p.minor, acc);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      if (oy0 + dy >= p.out_h) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        if (ox0 + dx >= p.out_w) continue;
+        store_vec<T>(outm + ((int64_t)(oy0 + dy) * p.out_w + ox0 + dx) * p.minor, acc[dy][dx]);
+      }
+    }
   }
+}
+
+template <typename T, int UP, int DOWN>
+int launch_fir4_quad(const void* in, void* out, const float* kern, const FirP& p, cudaStream_t st) {
+  constexpr int V = 16 / sizeof(T);
+  constexpr int YB = 4;
+  const int cv = p.minor / V;
+  const int bxs = (p.out_w + 1) / 2;
+  const int bygs = ((p.out_h + 1) / 2 + YB - 1) / YB;
+  const int64_t total = p.major * bygs * (int64_t)bxs * cv;
+  const int64_t blocks = (total + 255) / 256;
+  if (blocks >= (1LL << 31)) return MUDIFF_EUNSUPPORTED;
+  fir4_quad_kernel<T, UP, DOWN, YB><<<(unsigned)blocks, 256, 0, st>>>((const T*)in, (T*)out, kern, p, bxs, bygs);
+  return mudiff_launch_status();
 }
 
 template <typename T>
@@ -203,15 +264,11 @@ int launch_fir(const void* in, void* out, const float* kern, const FirP& p, cuda
   if (total == 0) return 0;
   const bool aligned = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
   if (p.minor % V == 0 && aligned && p.kh == 4 && p.kw == 4 && p.up_x == p.up_y && p.down_x == p.down_y &&
-      p.up_x <= 2 && p.down_x <= 2 && !(p.up_x == 2 && p.down_x == 2) && p.minor / V <= 256 &&
-      p.major * p.out_h < (1LL << 31)) {
-    const int cv = p.minor / V;
-    const int block = (256 / cv) * cv;
-    const unsigned rows = (unsigned)(p.major * p.out_h);
-    if (p.up_x == 2) fir4_nhwc_kernel<T, 2, 1><<<rows, block, 0, st>>>((const T*)in, (T*)out, kern, p);
-    else if (p.down_x == 2) fir4_nhwc_kernel<T, 1, 2><<<rows, block, 0, st>>>((const T*)in, (T*)out, kern, p);
-    else fir4_nhwc_kernel<T, 1, 1><<<rows, block, 0, st>>>((const T*)in, (T*)out, kern, p);
-    return mudiff_launch_status();
+      p.up_x <= 2 && p.down_x <= 2 && !(p.up_x == 2 && p.down_x == 2) &&
+      !(p.up_x == 2 && ((p.px0 | p.py0) & 1)) && p.px0 >= 0 && p.py0 >= 0) {
+    if (p.up_x == 2) return launch_fir4_quad<T, 2, 1>(in, out, kern, p, st);
+    if (p.down_x == 2) return launch_fir4_quad<T, 1, 2>(in, out, kern, p, st);
+    return launch_fir4_quad<T, 1, 1>(in, out, kern, p, st);
   }
   if (p.minor % V == 0 && aligned) {
     int grid = grid_for(total / V, 256);

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256, 3) gn_stats_kernel(const T* __restrict__ 
 // fixed stride -> no integer division in the streaming loop, 4 independent 16-byte loads in flight.
 #define GN_APPLY_PPB 1024
 template <typename TI, typename TO>
-__global__ void gn_apply_kernel(const TI* __restrict__ x0, int c0, int ld0, const TI* __restrict__ x1, int c1, int ld1,
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const TI* __restrict__ x0, int c0, int ld0, const TI* __restrict__ x1, int c1, int ld1,
                                 const double* __restrict__ st0, int st0_ld, const double* __restrict__ st1, int st1_ld,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int64_t gb_bstride,
                                 TO* __restrict__ out, int ld_out, int64_t hw, int groups, float eps, int act) {
@@ -149,6 +149,48 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x0, int c0, int ld0, cons
   TO* dst = out + (int64_t)b * hw * ld_out + ch;
   const int64_t p0 = (int64_t)blockIdx.x * GN_APPLY_PPB;
   int64_t p1 = p0 + GN_APPLY_PPB; if (p1 > hw) p1 = hw;
+  if constexpr (sizeof(TI) == sizeof(TO)) {
+    // same element size on both sides: 8 raw 16-byte loads in flight per thread (latency-bound otherwise: the
+    // kernel sits at ~3 blocks/SM), then convert -> scale/shift -> activation -> pack -> store one at a time
+    constexpr int U = 8;
+    int64_t p = p0 + lane;
+    for (; p + (int64_t)(U - 1) * lanes < p1; p += (int64_t)lanes * U) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) raw[u] = *reinterpret_cast<const uint4*>(src + (p + (int64_t)u * lanes) * ld);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float v[V];
+        const TI* e = reinterpret_cast<const TI*>(&raw[u]);
+        if constexpr (sizeof(TI) == 2) {
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+          for (int k = 0; k < V / 2; ++k) { const float2 f = __bfloat1622float2(h2[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[k] = Cvt<TI>::to_f(e[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float t = fmaf(v[k], sc[k], sh[k]);
+          if (act == MUDIFF_ACT_SILU) t = (sizeof(TO) == 4) ? silu_exact(t) : silu_f(t);
+          v[k] = t;
+        }
+        store_vec<TO>(dst + (p + (int64_t)u * lanes) * ld_out, v);
+      }
+    }
+    for (; p < p1; p += lanes) {
+      float v[V];
+      load_vec<TI>(src + p * ld, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float t = fmaf(v[k], sc[k], sh[k]);
+        if (act == MUDIFF_ACT_SILU) t = (sizeof(TO) == 4) ? silu_exact(t) : silu_f(t);
+        v[k] = t;
+      }
+      store_vec<TO>(dst + p * ld_out, v);
+    }
+  } else {
   constexpr int U = 4;
   for (int64_t p = p0 + lane; p < p1; p += (int64_t)lanes * U) {
     float v[U][V];
@@ -182,6 +224,7 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x0, int c0, int ld0, cons
         }
       }
     }
+  }
   }
 }
 

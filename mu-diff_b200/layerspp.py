@@ -147,13 +147,18 @@ class AttnBlockpp(nn.Module, layers.PackCache):
         qk = ops.conv([(hn_flat, 1)], w_qk, 2 * C, bias=b_qk, pad=0)      # [B,2C,1,L]
         # V^T[b] = W2^T (M = C rows) x hn[b]^T : A = weights (shared), "weights" = hn (per sample)
         vt = ops.conv([(w_v, 1)], hn, Lt, pad=0, a_batched=False, batch=B, w_bstride=Lt * C, w_ld=C)   # [B,L,1,C] == V^T [B][C][L]
-        q = qk[:, :C]
-        k_ptr_view = qk[:, C:]
-        s = ops.conv([(q, 1)], k_ptr_view, Lt, pad=0, alpha=float(int(C) ** (-0.5)),
-                     w_bstride=Lt * 2 * C, w_ld=2 * C)                     # [B,L,1,L] scores
-        ops.softmax_rows_(s.permute(0, 2, 3, 1).reshape(B * Lt, Lt))
-        o = ops.conv([(s, 1)], vt, C, pad=0, w_bstride=C * Lt, w_ld=Lt)   # [B,C,1,L]
-        o = o.permute(0, 2, 3, 1).reshape(B, H, W, C).permute(0, 3, 1, 2)
+        if ops.attention_supported(C, Lt, dt):
+            # fused QK^T -> softmax -> PV (flash-style, tcgen05): the [L, L] scores never reach HBM
+            o = ops.attention(qk, vt, B, Lt, C, float(int(C) ** (-0.5)))   # [B,L,C]
+            o = o.view(B, H, W, C).permute(0, 3, 1, 2)
+        else:
+            q = qk[:, :C]
+            k_ptr_view = qk[:, C:]
+            s = ops.conv([(q, 1)], k_ptr_view, Lt, pad=0, alpha=float(int(C) ** (-0.5)),
+                         w_bstride=Lt * 2 * C, w_ld=2 * C)                     # [B,L,1,L] scores
+            ops.softmax_rows_(s.permute(0, 2, 3, 1).reshape(B * Lt, Lt))
+            o = ops.conv([(s, 1)], vt, C, pad=0, w_bstride=C * Lt, w_ld=Lt)   # [B,C,1,L]
+            o = o.permute(0, 2, 3, 1).reshape(B, H, W, C).permute(0, 3, 1, 2)
         sc = ops.SQRT2_INV if self.skip_rescale else 1.0
         return ops.conv([(o, 1)], w_o, C, bias=b_o, pad=0, residual=x, alpha=sc, beta=sc, want_stats=True)
 

@@ -318,6 +318,25 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
     return out
 
 
+FUSED_ATTENTION = _os.environ.get('MUDIFF_FUSED_ATTN', '1') != '0'
+
+
+def attention_supported(c, lt, dtype) -> bool:
+    """Shapes the fused tcgen05 attention kernel takes (others use the unfused GEMM / softmax / GEMM kernels)."""
+    return FUSED_ATTENTION and dtype == torch.bfloat16 and c == 256 and lt % 128 == 0
+
+
+def attention(qk, vt, b, lt, c, scale):
+    """out[b] = softmax(Q K^T * scale) V with qk = [B, L, 2C] (q | k), vt = V^T [B, C, L] -> [B, L, C] (bf16).
+    One kernel: the [L, L] scores never leave the SM (backbones/layerspp.py:118-122 materialises them)."""
+    L.require_cuda(qk, vt)
+    out = torch.empty((b, lt, c), dtype=torch.bfloat16, device=qk.device)
+    rc = L.lib().mudiff_attention_tc(qk.data_ptr(), vt.data_ptr(), out.data_ptr(), b, lt, c, float(scale),
+                                     L.stream_ptr(qk.device))
+    L.check(rc, 'attention_tc')
+    return out
+
+
 # ---------------------------------------------------------------------------------
 # small dense / embeddings
 # ---------------------------------------------------------------------------------

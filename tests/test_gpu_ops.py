@@ -305,6 +305,60 @@ def test_conv_tc_batched_weights_qk(M):
     assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize('case', ['plain', 'growing_max', 'long'])
+def test_fused_attention_vs_fp32(M, case):
+    """mudiff_attention_tc == softmax(q k^T * C^-1/2) v (backbones/layerspp.py:118-122) on bf16-exact operands.
+    P is rounded to bf16 before the P V product and O is stored in bf16: 1.5e-2 * max|ref| absolute.
+    'growing_max' makes the row maxima grow by far more than 2^8 from key tile to key tile, which forces the
+    lazy accumulator rescale (tcgen05.ld -> scale -> tcgen05.st) on every tile."""
+    from mudiff_b200 import ops
+    torch.manual_seed(11)
+    B, Lt, C = (2, 2048, 256) if case == 'long' else (3, 512, 256)
+    q = torch.randn(B, Lt, C)
+    k = torch.randn(B, Lt, C)
+    v = torch.randn(B, Lt, C)
+    if case == 'growing_max':
+        q = q * 4
+        k = k * (1 + torch.arange(Lt).div(128, rounding_mode='floor').float())[None, :, None]
+    qk = torch.cat([q, k], dim=2).to(torch.bfloat16).cuda().contiguous()          # [B, L, 2C]
+    vb = v.to(torch.bfloat16)
+    vt = vb.transpose(1, 2).contiguous().cuda()                                   # [B, C, L]
+    scale = C ** -0.5
+    out = ops.attention(qk, vt, B, Lt, C, scale)
+    torch.cuda.synchronize()
+    qf, kf = qk[..., :C].double().cpu(), qk[..., C:].double().cpu()
+    ref = torch.softmax(qf @ kf.transpose(1, 2) * scale, dim=-1) @ vb.double()
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert err <= 1.5e-2 * max(ref.abs().max().item(), 1.0), err
+    # run-to-run determinism (fixed unit order, no atomics)
+    out2 = ops.attention(qk, vt, B, Lt, C, scale)
+    assert torch.equal(out, out2)
+
+
+def test_attention_block_fused_matches_unfused(M):
+    """AttnBlockpp with the fused kernel vs the unfused GEMM / softmax / GEMM path of the same module."""
+    from mudiff_b200 import ops, layerspp
+    torch.manual_seed(2)
+    blk = layerspp.AttnBlockpp(256, skip_rescale=True, init_scale=1.0).cuda()
+    with torch.no_grad():
+        for prm in blk.parameters():
+            if prm.dim() == 1:
+                prm.normal_(0, 0.1)
+        blk.GroupNorm_0.weight.add_(1.0)
+    x = ops.as_nhwc(torch.randn(2, 256, 32, 32, device='cuda').to(torch.bfloat16))
+    old = ops.FUSED_ATTENTION
+    try:
+        ops.FUSED_ATTENTION = True
+        with torch.no_grad():
+            a = blk(x).float()
+        ops.FUSED_ATTENTION = False
+        with torch.no_grad():
+            b = blk(x).float()
+    finally:
+        ops.FUSED_ATTENTION = old
+    assert (a - b).abs().max().item() <= 2e-2 * b.abs().max().item()
+
+
 def test_softmax_rows(M):
     from mudiff_b200 import ops
     torch.manual_seed(2)
