@@ -99,6 +99,13 @@ int mudiff_posterior_update(const float* x01, int64_t x01_bstride, const float* 
  * ------------------------------------------------------------------------------- */
 int mudiff_gn_stats(const void* x, int c, int ld, int dtype, int batch, int64_t hw,
                     double* chstats, int st_ld, int st_off, void* stream);
+/* Folded GroupNorm / AdaGN parameters table[b][c] = (gamma*rstd, beta - mean*gamma*rstd) (float pairs, [batch][c0+c1])
+ * from per-channel (sum, sumsq) statistics of one or two concatenated sources; consumed by mudiff_conv_tc's
+ * A-operand transform (a_xform). */
+int mudiff_gn_scale_shift(const double* st0, int st0_ld, int c0, const double* st1, int st1_ld, int c1,
+                          const float* gamma, const float* beta, int64_t gb_bstride, int batch, int64_t hw,
+                          int groups, float eps, float* table, void* stream);
+
 /* partial float[batch*tiles_per_image][n][2] (written by mudiff_conv_tc) -> chstats[b][st_off + c][2] */
 int mudiff_stats_finalize(const float* partial, int tiles_per_image, int n, double* chstats, int st_ld,
                           int st_off, int batch, void* stream);
@@ -158,11 +165,29 @@ typedef struct mudiff_conv_desc {
                               odd (y, x) outputs of the 'same' 3x3 conv and write them at ((y-1)/2,
                               (x-1)/2) of an [(h-1)/2, (w-1)/2] output: this IS the stride-2 VALID conv
                               of conv_downsample_2d (up_or_down_sampling.py:183) on the tensor cores */
+  /* mudiff_conv_tc only: A-operand transform.  a_xform[i] != NULL: segment i is read as
+   * act(x * scale + shift) with (scale, shift) float pairs a_xform[i][(b * a_xform_ld[i] + c) * 2 + {0,1}] -
+   * the GroupNorm / AdaGN + SiLU that precedes the conv (layerspp.py:293-314) applied to the staged tile in
+   * shared memory, so the normalised tensor is never stored.  Zero padding is applied AFTER the transform. */
+  const float* a_xform[3];
+  int32_t a_xform_ld[3];   /* row stride of the table in (scale, shift) pairs */
+  int32_t a_xform_act;     /* MUDIFF_ACT_NONE or MUDIFF_ACT_SILU */
 } mudiff_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit GEMM (bf16 in, fp32 accumulate).  Requires a_c[i] % 64 == 0,
  * n % 32 == 0, stride == 1.  Returns MUDIFF_EUNSUPPORTED otherwise. */
 int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream);
+
+/* Fused stem of ConvFeatBlock / ConvBlock / ConvBlock_GAP (backbones/layerspp.py:394-501):
+ * conv3x3(1 -> n) -> GroupNorm / AdaGN -> SiLU with the raw conv output never stored.  The GroupNorm statistics
+ * follow from second moments of the 1-channel input: mudiff_stem_moments writes double[batch][54]
+ * (9 patch sums + 45 patch products), mudiff_stem_conv_gn_act consumes them. */
+int mudiff_stem_moments(const float* x, int ld, int batch, int h, int w, double* moments, void* stream);
+int mudiff_stem_conv_gn_act(const float* x, int ld, const float* wt, const float* bias, const double* moments,
+                            const float* gamma, const float* beta, int64_t gb_bstride, int groups, float eps,
+                            int act, float* scale_shift /* workspace float[batch][n][2] */,
+                            void* out, int out_ld, int out_coff, int out_dtype,
+                            int batch, int h, int w, int n, void* stream);
 /* Planning only: out[0..9] = tile_h, tile_w, tiles_per_image, n_tile, tiles_per_unit, stationary_weights,
  * a_slots, b_slots, accumulator_stages, halo(seg0).  Callers size `stats` with out[2]. */
 int mudiff_conv_tc_query(const mudiff_conv_desc* d, int32_t* out);

@@ -33,6 +33,7 @@ class ConvDesc(C.Structure):
         ('alpha', C.c_float), ('beta', C.c_float), ('act', C.c_int32),
         ('out', C.c_void_p), ('out_ld', C.c_int32), ('out_coff', C.c_int32), ('out_dtype', C.c_int32),
         ('stats', C.c_void_p), ('stats_groups', C.c_int32), ('flags', C.c_int32),
+        ('a_xform', C.c_void_p * 3), ('a_xform_ld', C.c_int32 * 3), ('a_xform_act', C.c_int32),
     ]
 
 
@@ -48,6 +49,7 @@ PROTOTYPES = {
     'mudiff_fused_bias_act': [_P, _P, _P, _P, _I, _L, _I, _L, _I, _I, _F, _F, _P],
     'mudiff_posterior_update': [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _P, _I, _L, _P],
     'mudiff_gn_stats': [_P, _I, _I, _I, _I, _L, _P, _I, _I, _P],
+    'mudiff_gn_scale_shift': [_P, _I, _I, _P, _I, _I, _P, _P, _L, _I, _L, _I, _F, _P, _P],
     'mudiff_stats_finalize': [_P, _I, _I, _P, _I, _I, _I, _P],
     'mudiff_gn_apply': [_P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _I, _I, _I, _L, _I, _F, _I, _P],
     'mudiff_zero': [_P, _L, _P],
@@ -58,6 +60,8 @@ PROTOTYPES = {
     'mudiff_debug_dump': [C.POINTER(C.c_int32), _I],
     'mudiff_debug_selftest': [],
     'mudiff_conv_simt': [C.POINTER(ConvDesc), _I, _P],
+    'mudiff_stem_moments': [_P, _I, _I, _I, _I, _P, _P],
+    'mudiff_stem_conv_gn_act': [_P, _I, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'mudiff_softmax_rows': [_P, _P, _I, _L, _I, _F, _P],
     'mudiff_linear': [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'mudiff_timestep_embedding': [_P, _P, _I, _I, _F, _P],

@@ -3,6 +3,7 @@
 // fp32 products, which tcgen05 does not offer), and (2) the path for shapes the
 // tensor-core kernel does not take: Cin=1 stem convs, the Cout=1 head conv, the
 // stride-2 input-pyramid conv.  Same mudiff_conv_desc contract as mudiff_conv_tc.
+#include <string.h>
 #include "common.cuh"
 
 namespace {
@@ -283,6 +284,203 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
 }
 
 // ---------------------------------------------------------------------------------
+// Fused stem: conv3x3(1 -> N) -> GroupNorm / AdaGN -> SiLU without ever storing the raw conv output
+// (ConvFeatBlock / ConvBlock / ConvBlock_GAP, backbones/layerspp.py:394-501).  The GroupNorm statistics of a
+// Cin == 1 convolution follow from second moments of the INPUT: with the 9-vector patch x_t(p) (zero padded),
+//   sum_p y_c   = n b_c + sum_t w_ct s_t,                       s_t  = sum_p x_t(p)
+//   sum_p y_c^2 = n b_c^2 + 2 b_c sum_t w_ct s_t + w_c^T R w_c,  R_tu = sum_p x_t(p) x_u(p)
+// so one pass over the 1-channel image (4 B / pixel) replaces the statistics pass over the N-channel tensor
+// (2 N B / pixel), and the conv kernel applies scale/shift/activation in its epilogue: 1 write instead of
+// write + read + read + write.
+// ---------------------------------------------------------------------------------
+#define MOM_N 54                       // 9 sums + 45 upper-triangular products
+#define MOM_ROWS 16
+__global__ void __launch_bounds__(256) stem_moments_kernel(const float* __restrict__ x, int ld, int H, int W,
+                                                           double* __restrict__ moments, double* __restrict__ partial,
+                                                           unsigned int* __restrict__ tickets) {
+  const int b = blockIdx.y, chunks = gridDim.x;
+  const int y0 = blockIdx.x * MOM_ROWS, y1 = min(y0 + MOM_ROWS, H);
+  const float* img = x + (int64_t)b * H * W * ld;
+  float acc[MOM_N];
+#pragma unroll
+  for (int i = 0; i < MOM_N; ++i) acc[i] = 0.f;
+  for (int xx = threadIdx.x; xx < W; xx += blockDim.x) {
+    float v[3][3];                              // rolling window: rows y-1, y, y+1 at columns xx-1..xx+1
+    auto load_row = [&](int yy, float (&r)[3]) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int ix = xx - 1 + c;
+        r[c] = (yy >= 0 && yy < H && ix >= 0 && ix < W) ? __ldg(img + ((int64_t)yy * W + ix) * ld) : 0.f;
+      }
+    };
+    load_row(y0 - 1, v[0]);
+    load_row(y0, v[1]);
+    for (int y = y0; y < y1; ++y) {
+      load_row(y + 1, v[2]);
+      float pt[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) pt[t] = v[t / 3][t % 3];
+      int k = 9;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        acc[t] += pt[t];
+#pragma unroll
+        for (int u2 = t; u2 < 9; ++u2) { acc[k] = fmaf(pt[t], pt[u2], acc[k]); ++k; }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { v[0][c] = v[1][c]; v[1][c] = v[2][c]; }
+    }
+  }
+  // warp reduce (fp32, fixed order), then across the warps in double
+  __shared__ double sred[8][MOM_N];
+  __shared__ bool s_last;
+#pragma unroll
+  for (int i = 0; i < MOM_N; ++i) {
+    float a = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5][i] = (double)a;
+  }
+  __syncthreads();
+  double* mine = partial + ((int64_t)b * chunks + blockIdx.x) * MOM_N;
+  if (threadIdx.x < MOM_N) {
+    double a = 0.0;
+    for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) a += sred[w2][threadIdx.x];
+    mine[threadIdx.x] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[b], 1u);
+    s_last = (t == (unsigned int)chunks - 1);
+    if (s_last) tickets[b] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < MOM_N) {
+    double a = 0.0;
+    for (int c = 0; c < chunks; ++c) a += partial[((int64_t)b * chunks + c) * MOM_N + threadIdx.x];
+    moments[(int64_t)b * MOM_N + threadIdx.x] = a;
+  }
+}
+
+// per (image, channel) folded GroupNorm scale / shift of the conv output, from the input moments:
+// one block per image, one thread per channel.
+__global__ void stem_scale_shift_kernel(const double* __restrict__ moments, const float* __restrict__ wt,
+                                        const float* __restrict__ bias, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, int64_t gb_bstride, int n, int groups, float eps,
+                                        double cnt, float* __restrict__ scale_shift) {
+  __shared__ double s_cs[256][2];
+  __shared__ float s_mean[64], s_rstd[64];
+  const int b = blockIdx.x, c = threadIdx.x;
+  const int cpg = n / groups;
+  if (c < n) {
+    const double* m = moments + (int64_t)b * MOM_N;
+    double wc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wc[t] = (double)wt[c * 9 + t];
+    const double bc = bias ? (double)bias[c] : 0.0;
+    double lin = 0.0, quad = 0.0;
+    int k = 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      lin += wc[t] * m[t];
+#pragma unroll
+      for (int u2 = t; u2 < 9; ++u2) { quad += (u2 == t ? 1.0 : 2.0) * wc[t] * wc[u2] * m[k]; ++k; }
+    }
+    s_cs[c][0] = cnt * bc + lin;
+    s_cs[c][1] = cnt * bc * bc + 2.0 * bc * lin + quad;
+  }
+  __syncthreads();
+  if (c < groups) {
+    double a = 0.0, q = 0.0;
+    for (int i = 0; i < cpg; ++i) { a += s_cs[c * cpg + i][0]; q += s_cs[c * cpg + i][1]; }
+    const double nn = cnt * (double)cpg;
+    const double mu = a / nn;
+    double var = q / nn - mu * mu;
+    if (var < 0.0) var = 0.0;
+    s_mean[c] = (float)mu;
+    s_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  if (c < n) {
+    const int g = c / cpg;
+    const float ga = gamma ? gamma[(int64_t)b * gb_bstride + c] : 1.f;
+    const float be = beta ? beta[(int64_t)b * gb_bstride + c] : 0.f;
+    const float sc = ga * s_rstd[g];
+    scale_shift[((int64_t)b * n + c) * 2 + 0] = sc;
+    scale_shift[((int64_t)b * n + c) * 2 + 1] = be - s_mean[g] * sc;
+  }
+}
+
+// conv3x3(1 -> N) * scale[b][c] + shift[b][c] -> activation; structure of conv_stem_kernel with per-image folded weights.
+template <typename TO>
+__global__ void __launch_bounds__(256, 2) conv_stem_gn_kernel(SimtP p, const float* __restrict__ scale_shift) {
+  const int nv = p.n / 8;
+  const int n0 = (threadIdx.x % nv) * 8;
+  const int lane = threadIdx.x / nv, lanes = blockDim.x / nv;
+  if (lane >= lanes) return;
+  const float* wt = (const float*)p.wt;
+  const int ld = p.a_ld[0];
+  const int W = p.w, H = p.h;
+  const int64_t rows = (int64_t)p.batch * H;
+  float w[9][8], bs[8];
+  int cur_b = -1;
+  for (int64_t row = (int64_t)blockIdx.x * STEM_ROWS; row < rows && row < (int64_t)(blockIdx.x + 1) * STEM_ROWS; ++row) {
+    const int b = (int)(row / H), y = (int)(row - (int64_t)b * H);
+    if (b != cur_b) {
+      cur_b = b;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = n0 + j;
+        const float2 ss = *reinterpret_cast<const float2*>(scale_shift + ((int64_t)b * p.n + c) * 2);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w[t][j] = wt[c * 9 + t] * ss.x;
+        bs[j] = (p.bias ? p.bias[c] : 0.f) * ss.x + ss.y;
+      }
+    }
+    const float* in = (const float*)p.a[0] + (int64_t)b * H * W * ld;
+    const float* r0 = y > 0 ? in + (int64_t)(y - 1) * W * ld : nullptr;
+    const float* r1 = in + (int64_t)y * W * ld;
+    const float* r2 = y + 1 < H ? in + (int64_t)(y + 1) * W * ld : nullptr;
+    for (int x = lane * 2; x < W; x += lanes * 2) {
+      float v[3][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int ix = x - 1 + c;
+        const bool okx = ix >= 0 && ix < W;
+        v[0][c] = (okx && r0) ? __ldg(r0 + (int64_t)ix * ld) : 0.f;
+        v[1][c] = okx ? __ldg(r1 + (int64_t)ix * ld) : 0.f;
+        v[2][c] = (okx && r2) ? __ldg(r2 + (int64_t)ix * ld) : 0.f;
+      }
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        if (x + px >= W) break;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = bs[j];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) a = fmaf(v[t / 3][t % 3 + px], w[t][j], a);
+          if (p.act == MUDIFF_ACT_SILU) a = (sizeof(TO) == 4) ? silu_exact(a) : silu_f(a);
+          acc[j] = a;
+        }
+        const int64_t pix = row * W + x + px;
+        TO* op = (TO*)p.out + pix * p.out_ld + p.out_coff + n0;
+        if constexpr (sizeof(TO) == 2) {
+          store_vec<TO>(op, acc);
+        } else {
+          float lo[4] = {acc[0], acc[1], acc[2], acc[3]}, hi[4] = {acc[4], acc[5], acc[6], acc[7]};
+          store_vec<float>((float*)op, lo);
+          store_vec<float>((float*)op + 4, hi);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // head kernel: N == 1, 3x3 pad 1, stride 1, single segment, Cin % 64 == 0 (the nf->1 output conv, with the
 // tanh of ncsnpp_generator_adagn_feat.py:445 in the epilogue).  HBM-read bound: every input pixel is read from
 // global memory ONCE per strip.  A warp owns 30 output columns x HEAD_YR rows: lane l holds input column
@@ -449,6 +647,7 @@ extern "C" int mudiff_conv_simt(const mudiff_conv_desc* d, int dtype, void* stre
   if (d->stride != 1 && d->stride != 2) return MUDIFF_EINVAL;
   if (!d->wt || !d->out) return MUDIFF_EINVAL;
   if (d->stats) return MUDIFF_EUNSUPPORTED;
+  if (d->a_xform[0] || d->a_xform[1] || d->a_xform[2]) return MUDIFF_EUNSUPPORTED;   // tcgen05 kernel only
   SimtP p;
   int koff = 0;
   bool any9 = false;
@@ -477,4 +676,71 @@ extern "C" int mudiff_conv_simt(const mudiff_conv_desc* d, int dtype, void* stre
   if (dtype == MUDIFF_BF16 && d->out_dtype == MUDIFF_BF16) return launch_simt<__nv_bfloat16, __nv_bfloat16>(p, st);
   if (dtype == MUDIFF_BF16 && d->out_dtype == MUDIFF_F32) return launch_simt<__nv_bfloat16, float>(p, st);
   return MUDIFF_EUNSUPPORTED;
+}
+
+// scratch of the moments kernel (block partials + tickets), one stream of use per device
+static double* g_mom_partial[16] = {nullptr};
+static size_t g_mom_cap[16] = {0};
+static unsigned int* g_mom_tickets[16] = {nullptr};
+static int g_mom_tcap[16] = {0};
+
+// moments[b] = {s_t (9), R_tu for t <= u (45)} of the zero-padded 3x3 patches of the 1-channel image x[b] (fp32).
+extern "C" int mudiff_stem_moments(const float* x, int ld, int batch, int h, int w, double* moments, void* stream) {
+  if (!x || !moments || batch <= 0 || h <= 0 || w <= 0 || ld < 1) return MUDIFF_EINVAL;
+  if (batch > 65535) return MUDIFF_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
+  const int chunks = (h + MOM_ROWS - 1) / MOM_ROWS;
+  const size_t need = (size_t)batch * chunks * MOM_N;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (need > g_mom_cap[dev]) {
+    if (cs != cudaStreamCaptureStatusNone) return MUDIFF_EUNSUPPORTED;     // must be sized by a warm-up run
+    double* pnew = nullptr;
+    if (cudaMalloc(&pnew, need * 2 * sizeof(double)) != cudaSuccess) return (int)cudaGetLastError();
+    g_mom_partial[dev] = pnew; g_mom_cap[dev] = need * 2;
+  }
+  if (batch > g_mom_tcap[dev]) {
+    if (cs != cudaStreamCaptureStatusNone) return MUDIFF_EUNSUPPORTED;
+    const int cap = batch * 2 < 4096 ? 4096 : batch * 2;
+    unsigned int* t = nullptr;
+    if (cudaMalloc(&t, cap * sizeof(unsigned int)) != cudaSuccess) return (int)cudaGetLastError();
+    cudaMemset(t, 0, cap * sizeof(unsigned int));
+    g_mom_tickets[dev] = t; g_mom_tcap[dev] = cap;
+  }
+  stem_moments_kernel<<<dim3(chunks, batch), 256, 0, st>>>(x, ld, h, w, moments, g_mom_partial[dev], g_mom_tickets[dev]);
+  return mudiff_launch_status();
+}
+
+// out = act(GroupNorm_groups(conv3x3(x; wt, bias)) * gamma + beta) for a 1-channel fp32 input x [B, H, W] (pixel
+// stride ld), wt fp32 [n][9]; gamma/beta fp32 [B][...] with row stride gb_bstride (NULL = plain GroupNorm);
+// scale_shift = caller-provided float[batch][n][2] workspace (the folded per-image scale / shift).
+extern "C" int mudiff_stem_conv_gn_act(const float* x, int ld, const float* wt, const float* bias, const double* moments,
+                                       const float* gamma, const float* beta, int64_t gb_bstride, int groups, float eps,
+                                       int act, float* scale_shift, void* out, int out_ld, int out_coff, int out_dtype,
+                                       int batch, int h, int w, int n, void* stream) {
+  if (!x || !wt || !moments || !out || !scale_shift || batch <= 0 || h <= 0 || w <= 0 || n <= 0 || groups <= 0) return MUDIFF_EINVAL;
+  if (act != MUDIFF_ACT_NONE && act != MUDIFF_ACT_SILU) return MUDIFF_EINVAL;
+  if (n % 8 || n > 256 || n % groups || groups > 64 || out_ld % 8 || out_coff % 8 || ((uintptr_t)out % 16)) return MUDIFF_EUNSUPPORTED;
+  const int64_t rows = (int64_t)batch * h;
+  if (rows >= (1LL << 31)) return MUDIFF_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  stem_scale_shift_kernel<<<batch, 256, 0, st>>>(moments, wt, bias, gamma, beta, gb_bstride, n, groups, eps,
+                                                 (double)h * (double)w, scale_shift);
+  int rc = mudiff_launch_status();
+  if (rc) return rc;
+  SimtP p;
+  memset(&p, 0, sizeof(p));
+  p.a[0] = x; p.a_c[0] = 1; p.a_ld[0] = ld; p.a_taps[0] = 9; p.nseg = 1; p.a_batched = 1;
+  p.batch = batch; p.h = h; p.w = w; p.ho = h; p.wo = w; p.stride = 1; p.pad = 1;
+  p.wt = wt; p.ktot = 9; p.w_ld = 9; p.n = n; p.bias = bias; p.alpha = 1.f; p.act = act;
+  p.out = out; p.out_ld = out_ld; p.out_coff = out_coff;
+  const int nv = n / 8;
+  const int block = (256 / nv) * nv;
+  const unsigned grid = (unsigned)((rows + STEM_ROWS - 1) / STEM_ROWS);
+  if (out_dtype == MUDIFF_BF16) conv_stem_gn_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(p, scale_shift);
+  else if (out_dtype == MUDIFF_F32) conv_stem_gn_kernel<float><<<grid, block, 0, st>>>(p, scale_shift);
+  else return MUDIFF_EUNSUPPORTED;
+  return mudiff_launch_status();
 }

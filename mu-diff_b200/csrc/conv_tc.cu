@@ -24,6 +24,8 @@ namespace {
 
 constexpr int kMaxSlots = 16;
 constexpr int kThreads = 256;               // warps 0-3: A producer, B producer, MMA issuer of tile 0, MMA issuer of tile 1; warps 4-7: epilogue.
+constexpr int kThreadsXform = 384;          // + warps 8-11: A-operand transform (GroupNorm scale/shift + SiLU applied in shared memory)
+constexpr int kAReadyOff = 832;             // byte offset of the a_ready barriers inside the barrier block
 // One epilogue warp per TMEM lane quadrant.  Two warps per quadrant (8 epilogue warps, aligned or not) made
 // epilogue-bound GEMMs (N = 4096, K = 256) fault intermittently on B200 (~1 launch in 10, tools/stress_conv.py).
 constexpr uint32_t kSmemMax = 232448;       // 227 KB opt-in limit per CTA
@@ -52,6 +54,8 @@ struct TcParams {
   float alpha, beta; int act;
   void* out; int out_ld, out_coff;
   float* stats_partial;                       // [batch*tpi][n_total][2] or NULL
+  // A-operand transform: y = act(x * scale[b][c] + shift[b][c]) applied to the staged tile of segment s
+  const float* xform[3]; int xform_ld[3]; int xform_any, xform_act;
 };
 
 // ---------------------------------------------------------------------------------
@@ -221,7 +225,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 }
 
 template <bool kOutF32>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsXform, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW,
                const __grid_constant__ TcParams p) {
@@ -236,12 +240,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   uint64_t* tfull_bar = w_full + 1;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  uint64_t* a_ready = (uint64_t*)(smem + p.off_bar + kAReadyOff);   // transformed A tile ready (4 arrivals: one per transform warp)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], 4); }
     for (int i = 0; i < p.b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.MT); }     // one arrival per issuing warp
     for (int i = 0; i < 32; ++i) ((int*)(bar_block + kDbgRecOff))[i] = 0;
     mbar_init(w_full, 1);
@@ -363,7 +368,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (p.dbg_skew & (1 << me)) __nanosleep(2000);
         // my A tile of this group: next slot of MY ring (ring `me`, in order)
         const uint32_t sl = (uint32_t)me * (uint32_t)p.a_ring + a_slot, ph = a_phase;
-        if (active && !dry) mbar_wait(&a_full[sl], ph, bar_block, (int)(u - u_begin));
+        if (active && !dry) mbar_wait(p.xform_any ? &a_ready[sl] : &a_full[sl], ph, bar_block, (int)(u - u_begin));
         tc_fence_after();
         const uint32_t alo = a_lo_base + sl * a_step;
         const uint32_t hi_a = nb == 9 ? hi_a_halo : hi_b;
@@ -405,7 +410,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (p.acc_stages == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
       __syncwarp();
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // =========================== epilogue ===============================
     const int q = warp & 3;                        // TMEM lane quadrant this warp may read
     const int et = (warp - 4) * 32 + lane;         // epilogue thread index 0..127
@@ -552,6 +557,86 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (p.acc_stages == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
+    }
+  }
+
+  if (warp >= 8 && p.xform_any && !p.dbg_dry) {
+    // =========================== A-operand transform ===========================
+    // GroupNorm / AdaGN scale + shift and SiLU applied to the TMA-staged activation tile IN shared memory, between
+    // the TMA load and the MMAs: the normalised tensor is never written to HBM (it was a full read + write pass).
+    // 128 threads; thread t owns the logical 16-byte channel chunk c8 = t % 8 (its 8 (scale, shift) pairs live in
+    // registers) of rows t / 8 + 16 i; the physical chunk is c8 ^ (row & 7) (128-byte swizzle).  Pixels outside the
+    // image stay zero (the convolution pads AFTER the activation).
+    const int tx = threadIdx.x - 256;
+    const int c8 = tx & 7, r_first = tx >> 3;
+    uint32_t cnt0 = 0, cnt1 = 0;
+    const uint32_t ra = (uint32_t)p.a_ring;
+    for (long long u = u_begin; u < u_end; u += u_step) {
+      const Unit un = decode_unit(p, u);
+      for_each_group(p, [&](int s, int cb, int tap, int nb) {
+        for (int m = 0; m < un.count; ++m) {
+          const uint32_t k = m == 0 ? cnt0 : cnt1;
+          const uint32_t slot = (uint32_t)m * ra + k % ra;
+          mbar_wait(&a_full[slot], (k / ra) & 1u, bar_block, (int)k);
+          const float* tab = p.xform[s];
+          if (tab) {
+            const int r = un.r0 + m;
+            const int ty = r / p.tiles_x;
+            int oy = ty * p.tile_h, ox = (r - ty * p.tiles_x) * p.tile_w;
+            int rows, wpx;
+            if (nb == 9) { rows = (p.tile_w + 2) * (p.tile_h + 2); wpx = p.tile_w + 2; oy -= 1; ox -= 1; }
+            else {
+              rows = 128; wpx = p.tile_w;
+              if (p.seg_taps[s] == 9) { oy += tap / 3 - 1; ox += tap % 3 - 1; }
+            }
+            // this thread's 8 channels: (scale, shift) of the pre-activation, halved for silu(t) = h + h tanh(h), h = t/2
+            const float4* tp = reinterpret_cast<const float4*>(tab + ((int64_t)un.b * p.xform_ld[s] + cb * 64 + c8 * 8) * 2);
+            float sc[8], sh[8];
+            const float hf = p.xform_act == MUDIFF_ACT_SILU ? 0.5f : 1.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 v4 = __ldg(tp + i);
+              sc[2 * i] = v4.x * hf; sh[2 * i] = v4.y * hf; sc[2 * i + 1] = v4.z * hf; sh[2 * i + 1] = v4.w * hf;
+            }
+            uint8_t* base = smem + (size_t)slot * p.a_slot_bytes;
+            // four rows per trip (independent load -> MUFU -> store chains; one warp per scheduler has no other
+            // way to hide the latencies)
+            for (int rr0 = r_first; rr0 < rows; rr0 += 64) {
+              uint4 raw[4];
+              bool ok[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int rr = rr0 + 16 * j;
+                const int hy = rr / wpx, hx = rr - hy * wpx;
+                const int y = oy + hy, x = ox + hx;
+                ok[j] = rr < rows && y >= 0 && y < p.H && x >= 0 && x < p.W;
+                raw[j] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[j]) raw[j] = *reinterpret_cast<const uint4*>(base + rr * 128 + ((c8 ^ (rr & 7)) << 4));
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162* e = reinterpret_cast<__nv_bfloat162*>(&raw[j]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = __bfloat1622float2(e[i]);
+                  float h0 = fmaf(f.x, sc[2 * i], sh[2 * i]), h1 = fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1]);
+                  if (p.xform_act == MUDIFF_ACT_SILU) { h0 = fmaf(h0, tanh_approx(h0), h0); h1 = fmaf(h1, tanh_approx(h1), h1); }
+                  e[i] = __floats2bfloat162_rn(h0, h1);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int rr = rr0 + 16 * j;
+                if (ok[j]) *reinterpret_cast<uint4*>(base + rr * 128 + ((c8 ^ (rr & 7)) << 4)) = raw[j];
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[slot]);
+          if (m == 0) ++cnt0; else ++cnt1;
+        }
+      });
     }
   }
 
@@ -738,6 +823,16 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   p.residual = d->residual; p.res_ld = d->res_ld; p.alpha = d->alpha; p.beta = d->beta; p.act = d->act;
   p.out = d->out; p.out_ld = d->out_ld; p.out_coff = d->out_coff;
   p.stats_partial = (float*)d->stats;
+  p.xform_any = 0; p.xform_act = d->a_xform_act;
+  for (int s = 0; s < 3; ++s) {
+    p.xform[s] = s < d->nseg ? d->a_xform[s] : nullptr;
+    p.xform_ld[s] = s < d->nseg ? d->a_xform_ld[s] : 0;
+    if (p.xform[s]) {
+      if (((uintptr_t)p.xform[s] % 16) || p.xform_ld[s] % 2 || p.xform_ld[s] < d->a_c[s] || !d->a_batched) return MUDIFF_EUNSUPPORTED;
+      p.xform_any = 1;
+    }
+  }
+  if (p.xform_any && p.xform_act != MUDIFF_ACT_NONE && p.xform_act != MUDIFF_ACT_SILU) return MUDIFF_EINVAL;
   return 0;
 }
 
@@ -855,7 +950,8 @@ extern "C" int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream) {
     if (e != cudaSuccess) return (int)e;
     attr_set[dev][which] = true;
   }
-  if (which) conv_tc_kernel<true><<<grid, kThreads, smem_bytes, st>>>(maps[0], maps[1], maps[2], mapw, p);
-  else conv_tc_kernel<false><<<grid, kThreads, smem_bytes, st>>>(maps[0], maps[1], maps[2], mapw, p);
+  const int threads = p.xform_any ? kThreadsXform : kThreads;
+  if (which) conv_tc_kernel<true><<<grid, threads, smem_bytes, st>>>(maps[0], maps[1], maps[2], mapw, p);
+  else conv_tc_kernel<false><<<grid, threads, smem_bytes, st>>>(maps[0], maps[1], maps[2], mapw, p);
   return mudiff_launch_status();
 }

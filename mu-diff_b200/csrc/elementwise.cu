@@ -172,40 +172,46 @@ __global__ void tanh_kernel(const TS* __restrict__ x, TD* __restrict__ out, int6
 }
 
 // ---------------------------------------------------------------------------------
-// small dense layers: one warp per output feature j, loops over the batch in chunks of 8.
+// small dense layers: one warp per (output feature j, chunk of 8 batch rows): J * ceil(B/8) independent warps
+// (the layers are a serial chain of tiny GEMMs, so what matters is the latency of one launch: short
+// dependent-load chains and enough warps to cover the machine), 4 k-steps of loads in flight per lane.
 // ---------------------------------------------------------------------------------
-__global__ void linear_kernel(const float* __restrict__ in, int in_ld, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, int in_ld, const float* __restrict__ w,
                               const float* __restrict__ bias, float* __restrict__ out, int out_ld,
-                              int batch, int k, int j_total, int act_in, int act_out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                              int batch, int k, int j_total, int chunks, int act_in, int act_out) {
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= j_total) return;
-  const float* wr = w + (int64_t)warp * k;
-  const float bj = bias ? bias[warp] : 0.f;
-  for (int b0 = 0; b0 < batch; b0 += 8) {
-    float acc[8];
+  if (gw >= (int64_t)j_total * chunks) return;
+  const int j = (int)(gw / chunks);
+  const int b0 = (int)(gw % chunks) * 8;
+  const float* wr = w + (int64_t)j * k;
+  float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int kk = lane; kk < k; kk += 32) {
-      float wv = wr[kk];
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int kk = lane; kk < k; kk += 128) {
+    float wv[4], xv[4][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (b0 + i < batch) {
-          float xv = in[(int64_t)(b0 + i) * in_ld + kk];
-          acc[i] = fmaf(apply_act(xv, act_in), wv, acc[i]);
-        }
-      }
+    for (int u = 0; u < 4; ++u) {
+      const int kx = kk + 32 * u;
+      wv[u] = kx < k ? wr[kx] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[u][i] = (kx < k && b0 + i < batch) ? in[(int64_t)(b0 + i) * in_ld + kx] : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-    }
-    if (lane == 0) {
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(apply_act(xv[u][i], act_in), wv[u], acc[i]);
+  }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (b0 + i < batch) out[(int64_t)(b0 + i) * out_ld + warp] = apply_act(acc[i] + bj, act_out);
-    }
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  if (lane == 0) {
+    const float bj = bias ? bias[j] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (b0 + i < batch) out[(int64_t)(b0 + i) * out_ld + j] = apply_act(acc[i] + bj, act_out);
   }
 }
 
@@ -468,9 +474,11 @@ extern "C" int mudiff_tanh(const void* x, void* out, int dtype_in, int dtype_out
 extern "C" int mudiff_linear(const float* in, int in_ld, const float* w, const float* bias, float* out, int out_ld,
                              int batch, int k, int j, int act_in, int act_out, void* stream) {
   if (batch <= 0 || k <= 0 || j <= 0) return MUDIFF_EINVAL;
-  int warps_per_block = 8;
-  int grid = (j + warps_per_block - 1) / warps_per_block;
-  linear_kernel<<<grid, warps_per_block * 32, 0, (cudaStream_t)stream>>>(in, in_ld, w, bias, out, out_ld, batch, k, j, act_in, act_out);
+  const int chunks = (batch + 7) / 8;
+  const int64_t warps = (int64_t)j * chunks;
+  const int64_t grid = (warps + 7) / 8;
+  if (grid >= (1LL << 31)) return MUDIFF_EUNSUPPORTED;
+  linear_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(in, in_ld, w, bias, out, out_ld, batch, k, j, chunks, act_in, act_out);
   return mudiff_launch_status();
 }
 

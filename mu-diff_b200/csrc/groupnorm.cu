@@ -317,6 +317,39 @@ int launch_apply(const void* x0, int c0, int ld0, const void* x1, int c1, int ld
   return mudiff_launch_status();
 }
 
+// Folded GroupNorm / AdaGN parameters for consumers that apply the normalisation themselves (mudiff_conv_tc's
+// A-operand transform): table[b][c] = (scale, shift) with scale = gamma * rstd, shift = beta - mean * scale.
+// One block per image, one thread per channel; same double-precision group statistics as gn_apply_kernel.
+__global__ void gn_scale_shift_kernel(const double* __restrict__ st0, int st0_ld, int c0, const double* __restrict__ st1,
+                                      int st1_ld, int c1, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      int64_t gb_bstride, double hw, int groups, float eps, float* __restrict__ table) {
+  __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
+  const int C = c0 + c1, b = blockIdx.x, cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double a = 0.0, q = 0.0;
+    for (int i = 0; i < cpg; ++i) {
+      const int c = g * cpg + i;
+      const double* sp = c < c0 ? st0 + ((int64_t)b * st0_ld + c) * 2 : st1 + ((int64_t)b * st1_ld + (c - c0)) * 2;
+      a += sp[0]; q += sp[1];
+    }
+    const double cnt = hw * (double)cpg;
+    const double m = a / cnt;
+    double var = q / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)m;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float ga = gamma ? gamma[(int64_t)b * gb_bstride + c] : 1.f;
+    const float be = beta ? beta[(int64_t)b * gb_bstride + c] : 0.f;
+    const float sc = ga * s_rstd[g];
+    table[((int64_t)b * C + c) * 2 + 0] = sc;
+    table[((int64_t)b * C + c) * 2 + 1] = be - s_mean[g] * sc;
+  }
+}
+
 __global__ void gap_mean_kernel(const double* __restrict__ stats, float* __restrict__ out, int n, double inv) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)(stats[2 * i] * inv);
@@ -388,4 +421,16 @@ extern "C" int mudiff_gn_apply(const void* x0, int c0, int ld0, const double* st
   if (dtype_in == MUDIFF_BF16 && dtype_out == MUDIFF_F32) AP(__nv_bfloat16, float);
 #undef AP
   return MUDIFF_EUNSUPPORTED;
+}
+
+extern "C" int mudiff_gn_scale_shift(const double* st0, int st0_ld, int c0, const double* st1, int st1_ld, int c1,
+                                     const float* gamma, const float* beta, int64_t gb_bstride, int batch, int64_t hw,
+                                     int groups, float eps, float* table, void* stream) {
+  if (!st0 || !table || batch <= 0 || hw <= 0 || groups <= 0 || c0 <= 0 || c1 < 0) return MUDIFF_EINVAL;
+  if (!st1) c1 = 0;
+  const int C = c0 + c1;
+  if (C > GN_MAX_C || C % groups || groups > GN_MAX_C / 4) return MUDIFF_EUNSUPPORTED;
+  gn_scale_shift_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(st0, st0_ld, c0, st1, st1_ld, c1, gamma, beta, gb_bstride,
+                                                                   (double)hw, groups, eps, table);
+  return mudiff_launch_status();
 }

@@ -38,6 +38,12 @@ def _compute_dtype(t):
     return t.dtype if t.dtype in _F else torch.float32
 
 
+def _stem_fusable(conv, x):
+    """1 -> N stem conv whose GroupNorm + activation can be folded into the conv kernel (ops.stem_conv_gn_act)."""
+    return (ops.FUSED_STEM and conv.in_channels == 1 and x.shape[1] == 1 and conv.kernel_size == 3
+            and conv.out_channels % 8 == 0 and conv.out_channels <= 256)
+
+
 class AdaptiveGroupNorm(nn.Module):
     def __init__(self, num_groups, in_channel, style_dim):
         super().__init__()
@@ -50,6 +56,15 @@ class AdaptiveGroupNorm(nn.Module):
     def style_params(self, style):
         """Linear(style) -> [B, 2C] fp32: gamma = [:, :C], beta = [:, C:]."""
         return ops.linear(style, self.style.weight, self.style.bias)
+
+    def scale_shift(self, input, style, gb=None):
+        """(scale, shift) table [B, C, 2] of this AdaGN for consumers that apply it themselves (ops.conv xform)."""
+        srcs = _srcs(input)
+        L.require_cuda(*srcs)
+        gb = self.style_params(style) if gb is None else gb
+        c = self.in_channel
+        return ops.gn_scale_shift(srcs, [ops.get_chstats(t) for t in srcs], self.num_groups, gamma=gb, beta=gb[:, c:],
+                                  gb_bstride=gb.stride(0), eps=self.norm.eps)
 
     def forward(self, input, style, act=L.ACT_NONE, gb=None):
         srcs = _srcs(input)
@@ -256,15 +271,27 @@ class ResnetBlockBigGANpp_Adagn(nn.Module, layers.PackCache):
         seg_c = [t.shape[1] for t in xs]
         assert sum(seg_c) == self.in_ch, (seg_c, self.in_ch)
 
-        h = self.GroupNorm_0(tuple(xs), zemb, act=L.ACT_SILU, gb=gb0)      # AdaGN + SiLU, one pass
-        if self.up or self.down:
-            h = self._resample(h)
-            xs = [self._resample(t) for t in xs]
+        # bf16 tensor-core path: AdaGN + SiLU are applied by the conv kernel to its staged operand tiles
+        # (ops.conv xform) - the normalised tensor is never stored.  Not across a FIR resample (the FIR reads it).
+        fuse = (ops.FUSED_GN and dt == torch.bfloat16 and all(c % 64 == 0 for c in seg_c) and self.out_ch % 64 == 0)
         if tbias is None and temb is not None:
             tbias = ops.linear(temb, self.Dense_0.weight, self.Dense_0.bias, act_in=L.ACT_SILU)
-        h = ops.conv([(h, 9)], self.Conv_0.packed_weight(dt), self.out_ch, bias=self.Conv_0.bias_f32(),
-                     rowbias=tbias, want_stats=True)
-        h = self.GroupNorm_1(h, zemb, act=L.ACT_SILU, gb=gb1)
+        if fuse and not (self.up or self.down):
+            tab0 = self.GroupNorm_0.scale_shift(tuple(xs), zemb, gb=gb0)
+            offs = [0] + [sum(seg_c[:i + 1]) for i in range(len(seg_c) - 1)]
+            h = ops.conv([(t, 9, (tab0, o)) for t, o in zip(xs, offs)], self.Conv_0.packed_weight(dt, seg_c), self.out_ch,
+                         bias=self.Conv_0.bias_f32(), rowbias=tbias, want_stats=True)
+        else:
+            h = self.GroupNorm_0(tuple(xs), zemb, act=L.ACT_SILU, gb=gb0)      # AdaGN + SiLU, one pass
+            if self.up or self.down:
+                h = self._resample(h)
+                xs = [self._resample(t) for t in xs]
+            h = ops.conv([(h, 9)], self.Conv_0.packed_weight(dt), self.out_ch, bias=self.Conv_0.bias_f32(),
+                         rowbias=tbias, want_stats=True)
+        if fuse:
+            hseg = (h, 9, (self.GroupNorm_1.scale_shift(h, zemb, gb=gb1), 0))
+        else:
+            hseg = (self.GroupNorm_1(h, zemb, act=L.ACT_SILU, gb=gb1), 9)
         sc = ops.SQRT2_INV if self.skip_rescale else 1.0
         w1 = self.Conv_1.packed_weight(dt)
         if hasattr(self, 'Conv_2'):
@@ -274,9 +301,9 @@ class ResnetBlockBigGANpp_Adagn(nn.Module, layers.PackCache):
                               lambda: torch.cat([w1, c2.packed_weight(dt, seg_c)], dim=1).contiguous())
             bias = self._packed(('b12',), [self.Conv_1.bias, c2.bias],
                                 lambda: (self.Conv_1.bias + c2.bias).detach().float().contiguous())
-            return ops.conv([(h, 9)] + [(t, 1) for t in xs], wt, self.out_ch, bias=bias, alpha=sc, want_stats=True)
+            return ops.conv([hseg] + [(t, 1) for t in xs], wt, self.out_ch, bias=bias, alpha=sc, want_stats=True)
         res = xs[0] if len(xs) == 1 else ops.concat(xs)
-        return ops.conv([(h, 9)], w1, self.out_ch, bias=self.Conv_1.bias_f32(), residual=res, alpha=sc, beta=sc,
+        return ops.conv([hseg], w1, self.out_ch, bias=self.Conv_1.bias_f32(), residual=res, alpha=sc, beta=sc,
                         want_stats=True)
 
 
@@ -292,8 +319,12 @@ class ConvFeatBlock(nn.Module):
 
     def forward(self, x, compute_dtype=None, out=None, out_coff=0, stats_out=None):
         dt = compute_dtype or _compute_dtype(x)
-        h = self.conv1(x, compute_dtype=dt, want_stats=True)
-        h = self.group_norm(h, act=L.ACT_SILU)
+        if _stem_fusable(self.conv1, x):
+            h = ops.stem_conv_gn_act(x, self.conv1.packed_weight(torch.float32), self.conv1.bias_f32(),
+                                     self.group_norm.num_groups, eps=self.group_norm.norm.eps, act=L.ACT_SILU, out_dtype=dt)
+        else:
+            h = self.conv1(x, compute_dtype=dt, want_stats=True)
+            h = self.group_norm(h, act=L.ACT_SILU)
         return self.conv2(h, compute_dtype=dt, out=out, out_coff=out_coff, want_stats=True, stats_out=stats_out)
 
 
@@ -309,8 +340,15 @@ class ConvBlock(nn.Module):
 
     def forward(self, x, style=None, compute_dtype=None, out=None, out_coff=0):
         dt = compute_dtype or _compute_dtype(x)
-        h = self.conv1(x, compute_dtype=dt, want_stats=True)
-        h = self.group_norm(h, style, act=L.ACT_SILU)
+        if _stem_fusable(self.conv1, x):
+            gn = self.group_norm
+            gb = gn.style_params(style)
+            h = ops.stem_conv_gn_act(x, self.conv1.packed_weight(torch.float32), self.conv1.bias_f32(), gn.num_groups,
+                                     gamma=gb, beta=gb[:, gn.in_channel:], gb_bstride=gb.stride(0), eps=gn.norm.eps,
+                                     act=L.ACT_SILU, out_dtype=dt)
+        else:
+            h = self.conv1(x, compute_dtype=dt, want_stats=True)
+            h = self.group_norm(h, style, act=L.ACT_SILU)
         return self.conv2(h, compute_dtype=dt, out=out, out_coff=out_coff)
 
 
@@ -328,8 +366,12 @@ class ConvBlock_GAP(nn.Module):
 
     def forward(self, x, compute_dtype=None):
         dt = compute_dtype or _compute_dtype(x)
-        h = self.conv1(x, compute_dtype=dt, want_stats=True)
-        h = self.group_norm(h, act=L.ACT_SILU)
+        if _stem_fusable(self.conv1, x):
+            h = ops.stem_conv_gn_act(x, self.conv1.packed_weight(torch.float32), self.conv1.bias_f32(),
+                                     self.group_norm.num_groups, eps=self.group_norm.norm.eps, act=L.ACT_SILU, out_dtype=dt)
+        else:
+            h = self.conv1(x, compute_dtype=dt, want_stats=True)
+            h = self.group_norm(h, act=L.ACT_SILU)
         h = self.conv2(h, compute_dtype=dt)
         g = ops.gap(h)
         assert g.shape[1] == self.fc.in_features, f"GAP vector {g.shape[1]} != fc.in_features {self.fc.in_features}"

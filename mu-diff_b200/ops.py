@@ -188,6 +188,29 @@ def gn_apply(srcs, chstats, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-
     return out
 
 
+FUSED_GN = _os.environ.get('MUDIFF_FUSED_GN', '0') != '0'      # measured slower than the stand-alone gn_apply pass so far (A ring too shallow), see DESIGN.md
+
+
+def gn_scale_shift(srcs, chstats, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6):
+    """Folded GroupNorm / AdaGN parameters of the channel-concat of `srcs`: float [B, C, 2] = (scale, shift) with
+    GN(x)*gamma + beta == x*scale + shift.  Consumed by conv(..., segs=[(x, taps, (table, c_off))]) which applies
+    them (and the SiLU) to the staged activation tile instead of a separate full read + write pass."""
+    x0 = srcs[0]
+    b, c0, h, w = x0.shape
+    c1 = srcs[1].shape[1] if len(srcs) > 1 else 0
+    s0 = chstats[0]
+    s1 = chstats[1] if len(srcs) > 1 else None
+    table = torch.empty((b, c0 + c1, 2), dtype=torch.float32, device=x0.device)
+    rc = L.lib().mudiff_gn_scale_shift(s0.data_ptr(), s0.stride(0) // 2, c0,
+                                       s1.data_ptr() if s1 is not None else None,
+                                       s1.stride(0) // 2 if s1 is not None else 0, c1,
+                                       gamma.data_ptr() if gamma is not None else None,
+                                       beta.data_ptr() if beta is not None else None, gb_bstride,
+                                       b, h * w, groups, float(eps), table.data_ptr(), L.stream_ptr(x0.device))
+    L.check(rc, 'gn_scale_shift')
+    return table
+
+
 def group_norm(srcs, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_NONE, out_dtype=None):
     srcs = [s if is_nhwc_view(s) else as_nhwc(s) for s in srcs]
     return gn_apply(srcs, [get_chstats(s) for s in srcs], groups, gamma, beta, gb_bstride, eps, act, out_dtype)
@@ -210,13 +233,16 @@ def pack_conv_weight(weight: torch.Tensor, seg_channels, dtype) -> torch.Tensor:
 def tc_eligible(segs, n, stride, dtype) -> bool:
     if dtype != torch.bfloat16 or stride != 1 or n % 32:
         return False
-    return all(s.shape[1] % 64 == 0 for s, _ in segs)
+    return all(sg[0].shape[1] % 64 == 0 for sg in segs)
 
 
 def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta=0.0, act=L.ACT_NONE,
          out=None, out_coff=0, out_dtype=None, stride=1, pad=1, w_bstride=0, w_ld=0, a_batched=True,
-         batch=None, flags=0, force=None, want_stats=False, stats_out=None, dec2=False, fused_stats=None):
-    """Implicit-GEMM convolution.  segs = [(tensor NCHW-logical/channels-last, taps)], wt packed K-major.
+         batch=None, flags=0, force=None, want_stats=False, stats_out=None, dec2=False, fused_stats=None,
+         xform_act=L.ACT_SILU):
+    """Implicit-GEMM convolution.  segs = [(tensor NCHW-logical/channels-last, taps[, (table, c_off)])], wt packed
+    K-major; the optional third entry is a gn_scale_shift() table: the segment is read as
+    xform_act(x * scale + shift) (GroupNorm/AdaGN + SiLU fused into the operand path, tcgen05 kernel only).
     Chooses the tcgen05 kernel when eligible (bf16, Cin % 64 == 0, N % 32 == 0, stride 1), otherwise the
     CUDA-core kernel.  `force` in {None,'tc','simt'}."""
     x0 = segs[0][0]
@@ -237,13 +263,22 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
         out = empty_nhwc(b, n, ho, wo, out_dtype, dev)
     d = L.ConvDesc()
     keep = []
-    for i, (t, taps) in enumerate(segs):
+    any_xform = False
+    for i, sg in enumerate(segs):
+        t, taps = sg[0], sg[1]
         t = as_nhwc(t)
         keep.append(t)
         d.a[i] = t.data_ptr()
         d.a_c[i] = t.shape[1]
         d.a_ld[i] = _pix_ld(t)
         d.a_taps[i] = taps
+        if len(sg) > 2 and sg[2] is not None:
+            table, coff = sg[2]
+            keep.append(table)
+            d.a_xform[i] = table.data_ptr() + coff * 8
+            d.a_xform_ld[i] = table.shape[1]
+            any_xform = True
+    d.a_xform_act = xform_act if any_xform else L.ACT_NONE
     d.nseg = len(segs)
     d.a_batched = 1 if a_batched else 0
     d.batch, d.h, d.w = b, h, w
@@ -288,10 +323,12 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
         d.stats = partial.data_ptr()
     prof = None
     if _PROFILER is not None:
-        ktot = sum(t.shape[1] * taps for t, taps in segs)
+        ktot = sum(sg[0].shape[1] * sg[1] for sg in segs)
         prof = _PROFILER('conv_tc' if use_tc else 'conv_simt', 2.0 * b * ho * wo * n * ktot,
                          dict(n=n, ktot=ktot, pixels=b * ho * wo))
         prof.__enter__()
+    if any_xform and not use_tc:
+        raise RuntimeError("mu-diff_b200: the fused GroupNorm operand transform needs the tcgen05 conv kernel")
     if use_tc:
         L.check(L.lib().mudiff_conv_tc(C.byref(d), st), 'conv_tc')
     else:
@@ -315,6 +352,37 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
             cs = gn_stats(region, out=stats_out)
         if region is out:
             set_chstats(out, cs)
+    return out
+
+
+FUSED_STEM = _os.environ.get('MUDIFF_FUSED_STEM', '1') != '0'
+
+
+def stem_conv_gn_act(x, wt9, bias, groups, *, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_SILU,
+                     out_dtype=torch.bfloat16):
+    """act(GroupNorm(conv3x3(x))) for a 1-channel input (the stems of ConvFeatBlock / ConvBlock / ConvBlock_GAP,
+    backbones/layerspp.py:394-501) without storing the raw conv output: the GroupNorm statistics come from second
+    moments of the input image (mudiff_stem_moments), the conv kernel applies the folded scale / shift / activation.
+    wt9 = fp32 packed weights [n, 9]."""
+    L.require_cuda(x, wt9)
+    x = as_nhwc(x, torch.float32)
+    b, c, h, w = x.shape
+    if c != 1:
+        raise RuntimeError("mu-diff_b200: stem_conv_gn_act expects a 1-channel input")
+    n = wt9.shape[0]
+    dev = x.device
+    st = L.stream_ptr(dev)
+    mom = torch.empty((b, 54), dtype=torch.float64, device=dev)
+    L.check(L.lib().mudiff_stem_moments(x.data_ptr(), _pix_ld(x), b, h, w, mom.data_ptr(), st), 'stem_moments')
+    ss = torch.empty((b, n, 2), dtype=torch.float32, device=dev)
+    out = empty_nhwc(b, n, h, w, out_dtype, dev)
+    rc = L.lib().mudiff_stem_conv_gn_act(x.data_ptr(), _pix_ld(x), wt9.data_ptr(),
+                                         bias.data_ptr() if bias is not None else None, mom.data_ptr(),
+                                         gamma.data_ptr() if gamma is not None else None,
+                                         beta.data_ptr() if beta is not None else None, gb_bstride, groups, float(eps),
+                                         act, ss.data_ptr(), out.data_ptr(), _pix_ld(out), 0, L.dtype_code(out.dtype),
+                                         b, h, w, n, st)
+    L.check(rc, 'stem_conv_gn_act')
     return out
 
 

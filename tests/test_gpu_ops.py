@@ -273,6 +273,59 @@ def test_conv_tc_adversarial_schedules(M, skew, shape):
         assert (ref.float() - r32).abs().max().item() <= 2e-2 * max(r32.abs().max().item(), 1.0)
 
 
+XF_CASES = {
+    # C, taps, xform-per-segment, N, B, H, W, flags
+    'halo_c64':        dict(C=[64], taps=[9], xf=[True], N=64, B=2, H=32, W=32, flags=0),
+    'halo_ragged':     dict(C=[128], taps=[9], xf=[True], N=128, B=3, H=24, W=20, flags=0),
+    'pertap_ragged':   dict(C=[64], taps=[9], xf=[True], N=64, B=2, H=24, W=20, flags=2),
+    'concat_2src':     dict(C=[256, 64], taps=[9, 9], xf=[True, True], N=64, B=1, H=48, W=40, flags=0),
+    'with_shortcut':   dict(C=[64, 128, 64], taps=[9, 1, 1], xf=[True, False, False], N=64, B=2, H=32, W=32, flags=0),
+    'stream_n256':     dict(C=[256], taps=[9], xf=[True], N=256, B=2, H=32, W=32, flags=0),
+    'many_units':      dict(C=[64], taps=[9], xf=[True], N=64, B=8, H=128, W=128, flags=0),
+    'gemm_1x1':        dict(C=[128], taps=[1], xf=[True], N=128, B=2, H=16, W=16, flags=0),
+}
+
+
+@pytest.mark.parametrize('name', list(XF_CASES))
+def test_conv_tc_fused_groupnorm_operand(M, name):
+    """conv(act(x * scale + shift)) with the AdaGN scale/shift + SiLU applied by the conv kernel to its staged
+    operand tiles (a_xform) == the same conv on the explicitly normalised tensor.  shift != 0 checks that the zero
+    padding is applied AFTER the transform; ragged sizes check tile rows outside the image."""
+    from mudiff_b200 import ops
+    c = XF_CASES[name]
+    torch.manual_seed(9)
+    B, H, W, N = c['B'], c['H'], c['W'], c['N']
+    ctot = sum(c['C'])
+    table = torch.stack([1 + 0.3 * torch.randn(B, ctot), 0.5 * torch.randn(B, ctot)], dim=-1).cuda().contiguous()
+    segs_f, segs_u, ws, refs = [], [], [], 0
+    off = 0
+    for ci, taps, xf in zip(c['C'], c['taps'], c['xf']):
+        x = torch.randn(B, ci, H, W, device='cuda').to(torch.bfloat16)
+        k = 3 if taps == 9 else 1
+        w = (torch.randn(N, ci, k, k, device='cuda') / (ci * taps) ** 0.5).to(torch.bfloat16)
+        xn = x
+        if xf:
+            sc, sh = table[:, off:off + ci, 0], table[:, off:off + ci, 1]
+            xn = F.silu(x.float() * sc[:, :, None, None] + sh[:, :, None, None]).to(torch.bfloat16)
+        segs_f.append((ops.as_nhwc(x), taps, (table, off)) if xf else (ops.as_nhwc(x), taps))
+        segs_u.append((ops.as_nhwc(xn), taps))
+        ws.append(ops.pack_conv_weight(w, (ci,), torch.bfloat16))
+        refs = refs + F.conv2d(xn.double(), w.double(), padding=1 if taps == 9 else 0)
+        off += ci
+    wt = torch.cat(ws, dim=1).contiguous()
+    fused = ops.conv(segs_f, wt, N, out_dtype=torch.float32, flags=c['flags'], force='tc')
+    unfused = ops.conv(segs_u, wt, N, out_dtype=torch.float32, flags=c['flags'], force='tc')
+    torch.cuda.synchronize()
+    scale = max(refs.abs().max().item(), 1.0)
+    assert (unfused.double() - refs).abs().max().item() <= 2e-3 * scale
+    # the in-kernel transform rounds to bf16 like the explicit one but evaluates SiLU with tanh.approx: a few
+    # operand values land on the neighbouring bf16 -> 1e-2 * max|ref|
+    assert (fused.double() - refs).abs().max().item() <= 1e-2 * scale
+    # determinism
+    again = ops.conv(segs_f, wt, N, out_dtype=torch.float32, flags=c['flags'], force='tc')
+    assert torch.equal(fused, again)
+
+
 def test_conv_tc_decimated_equals_stride2_valid(M):
     """conv_downsample_2d's stride-2 VALID 3x3 conv (up_or_down_sampling.py:183) on the tensor cores:
     odd outputs of the pad-1 'same' conv."""
@@ -357,6 +410,30 @@ def test_attention_block_fused_matches_unfused(M):
     finally:
         ops.FUSED_ATTENTION = old
     assert (a - b).abs().max().item() <= 2e-2 * b.abs().max().item()
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('adagn', [False, True])
+def test_fused_stem_conv_gn_act(M, dtype, adagn):
+    """conv3x3(1 -> 64) -> GroupNorm(16) [AdaGN] -> SiLU with analytic statistics (input second moments) vs
+    F.conv2d + F.group_norm + silu in fp32.  fp32 output: 2e-5 absolute; bf16 output: bf16 rounding (1e-2)."""
+    from mudiff_b200 import ops
+    torch.manual_seed(4)
+    B, H, W, N, G = 3, 40, 56, 64, 16
+    x = torch.randn(B, 1, H, W) * 0.7 + 0.2
+    wgt = torch.randn(N, 1, 3, 3) / 3
+    bias = torch.randn(N) * 0.3
+    gb = torch.cat([1 + 0.2 * torch.randn(B, N), 0.3 * torch.randn(B, N)], dim=1)
+    y = F.group_norm(F.conv2d(x, wgt, bias, padding=1), G, eps=1e-6)
+    if adagn:
+        y = y * gb[:, :N, None, None] + gb[:, N:, None, None]
+    ref = F.silu(y)
+    gbd = gb.cuda()
+    kw = dict(gamma=gbd, beta=gbd[:, N:], gb_bstride=gbd.stride(0)) if adagn else {}
+    out = ops.stem_conv_gn_act(x.cuda(), ops.pack_conv_weight(wgt.cuda(), (1,), torch.float32), bias.cuda(), G,
+                               eps=1e-6, act=1, out_dtype=dtype, **kw)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2 * ref.abs().max().item()
+    assert (out.float().cpu() - ref).abs().max().item() <= tol
 
 
 def test_softmax_rows(M):
