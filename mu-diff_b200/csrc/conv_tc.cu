@@ -46,6 +46,7 @@ struct TcParams {
   int base_off_variant;
   int round_robin;                            // debug: interleaved instead of contiguous unit assignment
   int dbg_dry, dbg_noepi, dbg_nostore, dbg_noldtm;
+  int dbg_xf;                                 // timing ablations of the operand transform: 1 = barrier hop only, 2 = no activation
   int dbg_skew;                               // adversarial schedules: bit0 delay MMA warp 2, bit1 MMA warp 3, bit2 epilogue, bit3 A producer
   int dec2, Ho, Wo;                           // stride-2 VALID conv as a decimated 'same' conv: keep odd (y, x) only                     // debug: no operand traffic / no epilogue work (timing only)
   // epilogue
@@ -579,7 +580,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const uint32_t slot = (uint32_t)m * ra + k % ra;
           mbar_wait(&a_full[slot], (k / ra) & 1u, bar_block, (int)k);
           const float* tab = p.xform[s];
-          if (tab) {
+          if (tab && p.dbg_xf != 1) {
             const int r = un.r0 + m;
             const int ty = r / p.tiles_x;
             int oy = ty * p.tile_h, ox = (r - ty * p.tiles_x) * p.tile_w;
@@ -592,40 +593,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             // this thread's 8 channels: (scale, shift) of the pre-activation, halved for silu(t) = h + h tanh(h), h = t/2
             const float4* tp = reinterpret_cast<const float4*>(tab + ((int64_t)un.b * p.xform_ld[s] + cb * 64 + c8 * 8) * 2);
             float sc[8], sh[8];
-            const float hf = p.xform_act == MUDIFF_ACT_SILU ? 0.5f : 1.f;
+            const bool do_silu = p.xform_act == MUDIFF_ACT_SILU && p.dbg_xf != 2;
+            const float hf = do_silu ? 0.5f : 1.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 v4 = __ldg(tp + i);
               sc[2 * i] = v4.x * hf; sh[2 * i] = v4.y * hf; sc[2 * i + 1] = v4.z * hf; sh[2 * i + 1] = v4.w * hf;
             }
             uint8_t* base = smem + (size_t)slot * p.a_slot_bytes;
-            // four rows per trip (independent load -> MUFU -> store chains; one warp per scheduler has no other
-            // way to hide the latencies)
-            for (int rr0 = r_first; rr0 < rows; rr0 += 64) {
-              uint4 raw[4];
-              bool ok[4];
+            // six rows per trip: independent load -> convert -> FMA -> MUFU -> pack -> store chains (one warp per
+            // scheduler has no other way to hide the latencies); (hy, hx) advance incrementally (no divisions)
+            constexpr int RU = 6;
+            int hy = r_first / wpx, hx = r_first - hy * wpx;
+            const int dyy = 16 / wpx, dxx = 16 - dyy * wpx;          // advance of 16 rows in (hy, hx)
+            for (int rr0 = r_first; rr0 < rows; rr0 += 16 * RU) {
+              uint4 raw[RU];
+              bool ok[RU];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < RU; ++j) {
                 const int rr = rr0 + 16 * j;
-                const int hy = rr / wpx, hx = rr - hy * wpx;
                 const int y = oy + hy, x = ox + hx;
-                ok[j] = rr < rows && y >= 0 && y < p.H && x >= 0 && x < p.W;
+                ok[j] = rr < rows && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W;
                 raw[j] = make_uint4(0u, 0u, 0u, 0u);
                 if (ok[j]) raw[j] = *reinterpret_cast<const uint4*>(base + rr * 128 + ((c8 ^ (rr & 7)) << 4));
+                hy += dyy; hx += dxx;
+                if (hx >= wpx) { hx -= wpx; ++hy; }
               }
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < RU; ++j) {
                 __nv_bfloat162* e = reinterpret_cast<__nv_bfloat162*>(&raw[j]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float2 f = __bfloat1622float2(e[i]);
                   float h0 = fmaf(f.x, sc[2 * i], sh[2 * i]), h1 = fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1]);
-                  if (p.xform_act == MUDIFF_ACT_SILU) { h0 = fmaf(h0, tanh_approx(h0), h0); h1 = fmaf(h1, tanh_approx(h1), h1); }
+                  if (do_silu) { h0 = fmaf(h0, tanh_approx(h0), h0); h1 = fmaf(h1, tanh_approx(h1), h1); }
                   e[i] = __floats2bfloat162_rn(h0, h1);
                 }
               }
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < RU; ++j) {
                 const int rr = rr0 + 16 * j;
                 if (ok[j]) *reinterpret_cast<uint4*>(base + rr * 128 + ((c8 ^ (rr & 7)) << 4)) = raw[j];
               }
@@ -774,7 +780,11 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   // A ring depth: two groups of tiles for halo staging; plain 16 KB tiles (GEMM mode, 1x1 segments only)
   // get four groups - a 2-slot ring of plain tiles faulted intermittently on B200 in epilogue-bound GEMMs
   // (N = 4096, K = 256; root cause not understood), and the extra 32 KB are free there.
-  const int a_min = (!halo || (d->flags & 512)) ? 4 * MT : 2 * MT;
+  // With the A-operand transform a tile spends an extra ~0.5 us between its TMA load and its MMAs: the A rings
+  // must be three to four tiles deep per issuing warp (measured: two-deep rings made the fused launches 60 %
+  // slower, three-deep 13 %), so stationary weights are only taken when they leave that much room.
+  const bool xf = d->a_xform[0] || (d->nseg > 1 && d->a_xform[1]) || (d->nseg > 2 && d->a_xform[2]);
+  const int a_min = xf ? (MT == 2 ? 6 : 4) : ((!halo || (d->flags & 512)) ? 4 * MT : 2 * MT);
   p.stationary = 0;
   if (p.n_tiles == 1 && !p.w_batched && !(d->flags & 8) && (d->w_ld == 0 || d->w_ld == ktot) &&
       b_total + (uint32_t)a_min * p.a_slot_bytes <= avail && b_total < (1u << 20)) {
@@ -816,6 +826,7 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   p.dbg_nostore = (d->flags & 2048) ? 1 : 0;
   p.dbg_noldtm = (d->flags & 4096) ? 1 : 0;
   p.dbg_skew = (d->flags >> 16) & 15;
+  p.dbg_xf = (d->flags >> 20) & 3;
   p.dec2 = (d->flags & 32768) ? 1 : 0;
   p.Ho = p.dec2 ? (d->h - 1) / 2 : d->h;
   p.Wo = p.dec2 ? (d->w - 1) / 2 : d->w;

@@ -271,12 +271,15 @@ class ResnetBlockBigGANpp_Adagn(nn.Module, layers.PackCache):
         seg_c = [t.shape[1] for t in xs]
         assert sum(seg_c) == self.in_ch, (seg_c, self.in_ch)
 
-        # bf16 tensor-core path: AdaGN + SiLU are applied by the conv kernel to its staged operand tiles
-        # (ops.conv xform) - the normalised tensor is never stored.  Not across a FIR resample (the FIR reads it).
-        fuse = (ops.FUSED_GN and dt == torch.bfloat16 and all(c % 64 == 0 for c in seg_c) and self.out_ch % 64 == 0)
+        # bf16 tensor-core path: AdaGN + SiLU can be applied by the conv kernel to its staged operand tiles
+        # (ops.conv xform) - the normalised tensor is then never stored.  Not across a FIR resample (the FIR reads
+        # it), and only where it pays (ops.xform_profitable).
+        tc_ok = dt == torch.bfloat16 and all(c % 64 == 0 for c in seg_c) and self.out_ch % 64 == 0
+        fuse0 = tc_ok and not (self.up or self.down) and ops.xform_profitable(seg_c)
+        fuse1 = tc_ok and ops.xform_profitable([self.out_ch], len(xs) if hasattr(self, 'Conv_2') else 0)
         if tbias is None and temb is not None:
             tbias = ops.linear(temb, self.Dense_0.weight, self.Dense_0.bias, act_in=L.ACT_SILU)
-        if fuse and not (self.up or self.down):
+        if fuse0:
             tab0 = self.GroupNorm_0.scale_shift(tuple(xs), zemb, gb=gb0)
             offs = [0] + [sum(seg_c[:i + 1]) for i in range(len(seg_c) - 1)]
             h = ops.conv([(t, 9, (tab0, o)) for t, o in zip(xs, offs)], self.Conv_0.packed_weight(dt, seg_c), self.out_ch,
@@ -288,7 +291,7 @@ class ResnetBlockBigGANpp_Adagn(nn.Module, layers.PackCache):
                 xs = [self._resample(t) for t in xs]
             h = ops.conv([(h, 9)], self.Conv_0.packed_weight(dt), self.out_ch, bias=self.Conv_0.bias_f32(),
                          rowbias=tbias, want_stats=True)
-        if fuse:
+        if fuse1:
             hseg = (h, 9, (self.GroupNorm_1.scale_shift(h, zemb, gb=gb1), 0))
         else:
             hseg = (self.GroupNorm_1(h, zemb, act=L.ACT_SILU, gb=gb1), 9)

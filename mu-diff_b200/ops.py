@@ -15,6 +15,7 @@ SQRT2_INV = 1.0 / math.sqrt(2.0)
 
 import os as _os
 _ENV_FLAGS = 2 if _os.environ.get('MUDIFF_HALO', '1') == '0' else 0     # debug knob: forbid halo staging
+_ENV_FLAGS |= int(_os.environ.get('MUDIFF_XF_DBG', '0')) << 20        # timing ablations of the operand transform
 
 # Fused epilogue statistics (conv_tc butterfly reduction) are implemented and tested, but since the MMA issue
 # loop got fast they cost more than the stand-alone HBM-bound statistics pass for every N <= 256 (measured,
@@ -188,7 +189,19 @@ def gn_apply(srcs, chstats, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-
     return out
 
 
-FUSED_GN = _os.environ.get('MUDIFF_FUSED_GN', '0') != '0'      # measured slower than the stand-alone gn_apply pass so far (A ring too shallow), see DESIGN.md
+# GroupNorm/AdaGN + SiLU applied by the conv kernel to its staged operand tiles (conv_tc a_xform) instead of a separate
+# read + write pass.  Correct and tested, but NOT a win on B200 so far: the in-shared-memory transform adds a read +
+# write of every staged tile to shared-memory bandwidth that the N <= 128 tensor-core launches do not have to spare
+# (they are bound by the MMA operand reads): conv_tc +46 ms vs 48 ms of gn_apply saved per step when applied
+# everywhere, +5 ms vs 3 ms when restricted to single 64-channel segments (profiles/r01_fused_gn_ablation.md).
+#   MUDIFF_FUSED_GN = 0 (default) never, 1 single 64-channel 3x3 segment only, 2 wherever the kernel supports it
+FUSED_GN = int(_os.environ.get('MUDIFF_FUSED_GN', '0'))
+
+
+def xform_profitable(seg_channels, extra_segments=0) -> bool:
+    if FUSED_GN >= 2:
+        return True
+    return FUSED_GN == 1 and len(seg_channels) == 1 and seg_channels[0] == 64 and extra_segments == 0
 
 
 def gn_scale_shift(srcs, chstats, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6):
