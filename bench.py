@@ -45,26 +45,33 @@ def peaks():
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch from the committed `ncu --set full`
-    capture (profiles/r01_ncu_conv_tc_full_summary.json); None if the capture is not there."""
-    p = os.path.join(ROOT, 'profiles', 'r01_ncu_conv_tc_full_summary.json')
+    """Mean dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch, over ALL conv_tc launches of one step of
+    this workload (B = 64, 256^2), from the committed ncu capture profiles/r01_conv_tc_dram.csv (tools/profile_r01.sh).
+    None if the capture is not there."""
+    import csv
+    import gzip
+    p = os.path.join(ROOT, 'profiles', 'r01_conv_tc_dram.csv')
+    if not os.path.exists(p) and os.path.exists(p + '.gz'):
+        p += '.gz'
     if not os.path.exists(p):
-        return None, "no ncu --set full capture committed"
-    tot, n = 0.0, 0
-    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-    for rec in json.load(open(p)):
-        try:
-            b = 0.0
-            for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
-                v, u = rec[k].split()
-                b += float(v) * scale.get(u, 1.0)
-            tot += b
-            n += 1
-        except Exception:
-            pass
-    if not n:
-        return None, "capture unreadable"
-    return tot / n, f"mean DRAM bytes per conv_tc launch over the {n} launches of the committed capture (taken at batch 8; launch shapes differ)"
+        return None, "no ncu capture committed"
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+    per = {}
+    try:
+        rows = list(csv.reader(gzip.open(p, 'rt') if p.endswith('.gz') else open(p)))
+        hdr = next(i for i, r in enumerate(rows) if 'Metric Name' in r)
+        h = rows[hdr]
+        ki, mi, ui, vi = h.index('ID'), h.index('Metric Name'), h.index('Metric Unit'), h.index('Metric Value')
+        for r in rows[hdr + 1:]:
+            if len(r) <= vi or not r[mi].startswith('dram__bytes'):
+                continue
+            per[r[ki]] = per.get(r[ki], 0.0) + float(r[vi].replace(',', '')) * scale.get(r[ui], 1.0)
+    except Exception as e:                       # noqa: BLE001
+        return None, f"capture unreadable: {e}"
+    if not per:
+        return None, "capture has no dram__bytes rows"
+    return sum(per.values()) / len(per), (f"mean DRAM bytes (read + write) per conv_tc launch over the {len(per)} conv_tc launches "
+                                          "of one eager step of this workload, ncu capture profiles/r01_conv_tc_dram.csv")
 
 
 class ClockSampler(threading.Thread):

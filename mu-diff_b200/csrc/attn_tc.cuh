@@ -77,15 +77,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long u_begin = (p.total_units * (long long)blockIdx.x) / gridDim.x;
-  const long long u_end = (p.total_units * (long long)(blockIdx.x + 1)) / gridDim.x;
+  // strided unit assignment: at any time the grid works on ~gridDim.x consecutive query tiles = 4-5 images, so the K / V^T
+  // tiles every query tile of an image re-reads (4 MB per image) stay in L2.  (Contiguous ranges spread the CTAs over all
+  // 64 images at once: 256 MB of K / V^T, half of the re-reads missed L2 - 4.0 GB of DRAM traffic for 0.54 GB of operands.)
+  const long long u_begin = blockIdx.x, u_end = p.total_units, u_step = gridDim.x;
   const int nk = p.nk;
 
   if (warp == 0) {
     // ===================== Q / K producer =====================
     if (lane == 0) {
       uint32_t qc = 0, kc = 0;
-      for (long long u = u_begin; u < u_end; ++u) {
+      for (long long u = u_begin; u < u_end; u += u_step) {
         const int b = (int)(u / p.qtiles), q0 = (int)(u % p.qtiles) * 128;
         mbar_wait(&bar[AB_QEMPTY], (qc & 1u) ^ 1u, bar_block, (int)qc);
         mbar_expect_tx(&bar[AB_QFULL], 65536u);
@@ -104,7 +106,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant_
     // ===================== V^T producer =====================
     if (lane == 0) {
       uint32_t vc = 0;
-      for (long long u = u_begin; u < u_end; ++u) {
+      for (long long u = u_begin; u < u_end; u += u_step) {
         const int b = (int)(u / p.qtiles);
         for (int j = 0; j < nk; ++j) {
           mbar_wait(&bar[AB_VEMPTY], (vc & 1u) ^ 1u, bar_block, (int)vc);
@@ -140,7 +142,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant_
       }
       ++kc; ++sc;
     };
-    for (long long u = u_begin; u < u_end; ++u) {
+    for (long long u = u_begin; u < u_end; u += u_step) {
       mbar_wait(&bar[AB_QFULL], qc & 1u, bar_block, (int)qc);
       tc_fence_after();
       issue_qk();
@@ -175,7 +177,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant_
     uint8_t* prow = smem + kAttnPs + row * 128;
     const int rsw = row & 7;
     uint32_t tcount = 0;                       // key tiles processed by this CTA so far (== S / P / PV sequence number)
-    for (long long u = u_begin; u < u_end; ++u) {
+    for (long long u = u_begin; u < u_end; u += u_step) {
       const int b = (int)(u / p.qtiles), q0 = (int)(u % p.qtiles) * 128;
       float m_used = 0.f, l = 0.f;
       for (int j = 0; j < nk; ++j, ++tcount) {

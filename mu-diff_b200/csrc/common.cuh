@@ -76,6 +76,13 @@ __device__ __forceinline__ void store_vec<__nv_bfloat16>(__nv_bfloat16* p, const
   *reinterpret_cast<uint4*>(p) = raw;
 }
 
+// packed fp32 pairs: Blackwell's FFMA2 (fma.rn.f32x2) issues two fp32 FMAs per instruction - the FFMA-issue-bound
+// kernels (1-channel stems, head conv, FIR) keep their accumulators and weights as register pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
 __device__ __forceinline__ float silu_f(float x) { const float h = 0.5f * x; return fmaf(h, tanh_approx(h), h); }
 __device__ __forceinline__ float sigmoid_f(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 // exact-ish variants for the fp32 parity path

@@ -425,19 +425,19 @@ __global__ void __launch_bounds__(256, 2) conv_stem_gn_kernel(SimtP p, const flo
   const int ld = p.a_ld[0];
   const int W = p.w, H = p.h;
   const int64_t rows = (int64_t)p.batch * H;
-  float w[9][8], bs[8];
+  f32x2 w2[9][4], bs2[4];                       // channel pairs (n0 + 2j, n0 + 2j + 1): FFMA2
   int cur_b = -1;
   for (int64_t row = (int64_t)blockIdx.x * STEM_ROWS; row < rows && row < (int64_t)(blockIdx.x + 1) * STEM_ROWS; ++row) {
     const int b = (int)(row / H), y = (int)(row - (int64_t)b * H);
     if (b != cur_b) {
       cur_b = b;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = n0 + j;
-        const float2 ss = *reinterpret_cast<const float2*>(scale_shift + ((int64_t)b * p.n + c) * 2);
+      for (int j = 0; j < 4; ++j) {
+        const int c = n0 + 2 * j;
+        const float4 ss = *reinterpret_cast<const float4*>(scale_shift + ((int64_t)b * p.n + c) * 2);   // sc0 sh0 sc1 sh1
 #pragma unroll
-        for (int t = 0; t < 9; ++t) w[t][j] = wt[c * 9 + t] * ss.x;
-        bs[j] = (p.bias ? p.bias[c] : 0.f) * ss.x + ss.y;
+        for (int t = 0; t < 9; ++t) w2[t][j] = pack2(wt[c * 9 + t] * ss.x, wt[(c + 1) * 9 + t] * ss.z);
+        bs2[j] = pack2((p.bias ? p.bias[c] : 0.f) * ss.x + ss.y, (p.bias ? p.bias[c + 1] : 0.f) * ss.z + ss.w);
       }
     }
     const float* in = (const float*)p.a[0] + (int64_t)b * H * W * ld;
@@ -459,12 +459,15 @@ __global__ void __launch_bounds__(256, 2) conv_stem_gn_kernel(SimtP p, const flo
         if (x + px >= W) break;
         float acc[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float a = bs[j];
+        for (int j = 0; j < 4; ++j) {
+          f32x2 a = bs2[j];
 #pragma unroll
-          for (int t = 0; t < 9; ++t) a = fmaf(v[t / 3][t % 3 + px], w[t][j], a);
-          if (p.act == MUDIFF_ACT_SILU) a = (sizeof(TO) == 4) ? silu_exact(a) : silu_f(a);
-          acc[j] = a;
+          for (int t = 0; t < 9; ++t) { const float xv = v[t / 3][t % 3 + px]; a = fma2(pack2(xv, xv), w2[t][j], a); }
+          unpack2(a, acc[2 * j], acc[2 * j + 1]);
+        }
+        if (p.act == MUDIFF_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = (sizeof(TO) == 4) ? silu_exact(acc[j]) : silu_f(acc[j]);
         }
         const int64_t pix = row * W + x + px;
         TO* op = (TO*)p.out + pix * p.out_ld + p.out_coff + n0;
@@ -533,9 +536,9 @@ __global__ void __launch_bounds__(256, 2) conv_head_kernel(SimtP p, int xchunks,
   uint4 nxt[NV];
   fetch(y0 - 1, 0, nxt);
   for (int yy = y0 - 1; yy <= y1; ++yy) {
-    float P[9];
+    f32x2 P2[9];                                 // per-tap dot products, even / odd channels in the two halves (FFMA2)
 #pragma unroll
-    for (int t = 0; t < 9; ++t) P[t] = 0.f;
+    for (int t = 0; t < 9; ++t) P2[t] = pack2(0.f, 0.f);
     for (int cb = 0; cb < nblk; ++cb) {
       __syncwarp();
 #pragma unroll
@@ -560,12 +563,15 @@ __global__ void __launch_bounds__(256, 2) conv_head_kernel(SimtP p, int xchunks,
 #pragma unroll
           for (int k4 = 0; k4 < V; k4 += 4) {
             const float4 w4 = *reinterpret_cast<const float4*>(wb + t * C + vv * V + k4);     // warp-uniform: broadcast
-            P[t] = fmaf(v[k4 + 0], w4.x, P[t]); P[t] = fmaf(v[k4 + 1], w4.y, P[t]);
-            P[t] = fmaf(v[k4 + 2], w4.z, P[t]); P[t] = fmaf(v[k4 + 3], w4.w, P[t]);
+            P2[t] = fma2(pack2(v[k4 + 0], v[k4 + 1]), pack2(w4.x, w4.y), P2[t]);
+            P2[t] = fma2(pack2(v[k4 + 2], v[k4 + 3]), pack2(w4.z, w4.w), P2[t]);
           }
         }
       }
     }
+    float P[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { float lo, hi; unpack2(P2[t], lo, hi); P[t] = lo + hi; }
     // P[(dy+1)*3 + (dx+1)] is this pixel's contribution to out(yy - dy, x - dx)
     float q[3];
 #pragma unroll

@@ -162,7 +162,7 @@ template <int UP, int DOWN> struct Fir4Geom {
 };
 
 template <typename T, int UP, int DOWN, int YB>
-__global__ void __launch_bounds__(256) fir4_quad_kernel(const T* __restrict__ in, T* __restrict__ out,
+__global__ void __launch_bounds__(256, 4) fir4_quad_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                         const float* __restrict__ kern, FirP p, int bxs, int bygs) {
   using G = Fir4Geom<UP, DOWN>;
   constexpr int V = 16 / sizeof(T);
@@ -192,13 +192,13 @@ __global__ void __launch_bounds__(256) fir4_quad_kernel(const T* __restrict__ in
     const int oy0 = (byg * YB + yb) * 2;
     if (oy0 >= p.out_h) break;
     const int iy0 = UP == 2 ? (oy0 - p.py0) / 2 : oy0 * DOWN - p.py0;
-    float acc[2][2][V];
+    f32x2 acc[2][2][V / 2];                    // channel pairs: FFMA2
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 2; ++b)
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[a][b][i] = 0.f;
+        for (int i = 0; i < V / 2; ++i) acc[a][b][i] = pack2(0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       const int iy = iy0 + r;
@@ -212,10 +212,10 @@ __global__ void __launch_bounds__(256) fir4_quad_kernel(const T* __restrict__ in
       }
 #pragma unroll
       for (int s2 = 0; s2 < NR; ++s2) {
-        float v[V];
+        f32x2 v2[V / 2];
         const T* e = reinterpret_cast<const T*>(&raw[s2]);
 #pragma unroll
-        for (int i = 0; i < V; ++i) v[i] = Cvt<T>::to_f(e[i]);
+        for (int i = 0; i < V / 2; ++i) v2[i] = pack2(Cvt<T>::to_f(e[2 * i]), Cvt<T>::to_f(e[2 * i + 1]));
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
           const int ky = G::tap(dy, r);
@@ -225,8 +225,9 @@ __global__ void __launch_bounds__(256) fir4_quad_kernel(const T* __restrict__ in
             const int kx = G::tap(dx, s2);
             if (kx < 0) continue;
             const float w = kf[ky * 4 + kx];
+            const f32x2 ww = pack2(w, w);
 #pragma unroll
-            for (int i = 0; i < V; ++i) acc[dy][dx][i] = fmaf(w, v[i], acc[dy][dx][i]);
+            for (int i = 0; i < V / 2; ++i) acc[dy][dx][i] = fma2(ww, v2[i], acc[dy][dx][i]);
           }
         }
       }
@@ -237,7 +238,10 @@ __global__ void __launch_bounds__(256) fir4_quad_kernel(const T* __restrict__ in
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
         if (ox0 + dx >= p.out_w) continue;
-        store_vec<T>(outm + ((int64_t)(oy0 + dy) * p.out_w + ox0 + dx) * p.minor, acc[dy][dx]);
+        float o[V];
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) unpack2(acc[dy][dx][i], o[2 * i], o[2 * i + 1]);
+        store_vec<T>(outm + ((int64_t)(oy0 + dy) * p.out_w + ox0 + dx) * p.minor, o);
       }
     }
   }
