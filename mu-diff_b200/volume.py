@@ -62,6 +62,15 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int, int]:
     return lo, min(n, lo + per), per
 
 
+def balanced_batch(n_local: int, max_batch: int = 64) -> int:
+    """Batch size that splits a shard of n_local slices into equal batches of at most max_batch (a fixed-batch CUDA
+    graph then wastes at most one padded row per batch instead of up to max_batch - 1)."""
+    if n_local <= 0:
+        return 1
+    k = (n_local + max_batch - 1) // max_batch
+    return (n_local + k - 1) // k
+
+
 def slice_seed(seed: int, volume: int, index: int) -> int:
     return (int(seed) * 1000003 + int(volume) * 8191 + int(index) * 131 + 17) % (2 ** 63 - 1)
 
@@ -83,35 +92,135 @@ def draw_slice_noise(seed, volume, indices: Sequence[int], size, nz, n_time, dev
     return x_init, latents, noises
 
 
-def predict_slices_sharded(sample_fn: Callable, conds: Sequence[torch.Tensor], *, seed: int = 0, volume: int = 0,
-                           nz: int = 100, n_time: int = 4, batch: int = 64, device=None,
-                           group=None, gather: bool = True) -> torch.Tensor:
-    """Sample all N slices of one volume across the ranks of `group`.
+def predict_volumes_sharded(sample_fn: Callable, cond_volumes: Sequence[Sequence[torch.Tensor]], *, seed: int = 0,
+                            first_volume: int = 0, nz: int = 100, n_time: int = 4, batch: int = 64, device=None,
+                            group=None, gather: bool = True, prefetch: bool = True) -> List[torch.Tensor]:
+    """Sample every slice of several volumes across the ranks of `group`.
 
-    conds: n_cond tensors [N, 1, H, W] in [-1, 1] (same on every rank; only the local shard is used).
-    sample_fn(conds_batch, x_init, latents, noises) -> [b, 1, H, W]: the 4-step sampler
-    (e.g. `lambda c, x, z, e: sample_from_model(co, g1, c[0], g2, c[1], c[2], 4, x, None, opt, latents=z, noises=e)`).
-    Returns [N, 1, H, W] in [0, 1] ((x+1)/2 clamped, test_volume.py:285) on every rank if `gather`.
-    """
-    n = conds[0].shape[0]
-    hw = tuple(conds[0].shape[-2:])
-    device = device if device is not None else conds[0].device
+    cond_volumes[v] = n_cond tensors [N_v, 1, H, W] in [-1, 1] (same on every rank; only the local shard is used).
+    sample_fn(conds_batch, x_init, latents, noises) -> [b, 1, H, W]: the 4-step sampler, e.g. a GraphSliceSampler or
+    `lambda c, x, z, e: sample_from_model(co, g1, c[0], g2, c[1], c[2], 4, x, None, opt, latents=z, noises=e)`.
+    Every volume is split into contiguous shards of ceil(N_v / G) slices; a rank walks its shards batch by batch.
+    With `prefetch` the inputs of the NEXT batch (host->device copy of the conditioning slices, per-slice noise
+    draws) are produced on a side stream while the current batch is being sampled, across volume boundaries too -
+    with 8 GPUs a rank has one batch of ~20 slices per volume and this host/RNG work would otherwise be serial.
+    Returns one [N_v, 1, H, W] tensor per volume, in [0, 1] ((x+1)/2 clamped, test_volume.py:285), on every rank if
+    `gather` (ONE all-gather per volume - the only collective of the path), else the padded local shard."""
+    if not cond_volumes:
+        return []
+    device = torch.device(device) if device is not None else cond_volumes[0][0].device
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    lo, hi, per = shard_bounds(n, world, rank)
-    local = torch.zeros(per, 1, hw[0], hw[1], device=device)        # padded shard (last rank may be short)
-    for b0 in range(lo, hi, batch):
-        b1 = min(hi, b0 + batch)
-        idx = list(range(b0, b1))
-        cb = [c[b0:b1].to(device, non_blocking=True) for c in conds]
-        x_init, latents, noises = draw_slice_noise(seed, volume, idx, hw, nz, n_time, device)
+    cuda = device.type == 'cuda'
+    main = torch.cuda.current_stream(device) if cuda else None
+    side = torch.cuda.Stream(device=device) if (cuda and prefetch) else None
+
+    items = []                                   # (volume position, b0, b1) of this rank, in order
+    bounds = []
+    for v, conds in enumerate(cond_volumes):
+        lo, hi, per = shard_bounds(conds[0].shape[0], world, rank)
+        bounds.append((lo, hi, per))
+        for b0 in range(lo, hi, batch):
+            items.append((v, b0, min(hi, b0 + batch)))
+
+    def prepare(item):
+        v, b0, b1 = item
+        conds = cond_volumes[v]
+        hw = tuple(conds[0].shape[-2:])
+        ctx = torch.cuda.stream(side) if side is not None else _null_ctx()
+        with ctx:
+            cb = [c[b0:b1].to(device, non_blocking=True) for c in conds]
+            x_init, latents, noises = draw_slice_noise(seed, first_volume + v, list(range(b0, b1)), hw, nz, n_time, device)
+            ev = side.record_event() if side is not None else None
+        if side is not None:
+            for t in cb + [x_init] + latents + noises:
+                t.record_stream(main)
+        return cb, x_init, latents, noises, ev
+
+    outs: List[Optional[torch.Tensor]] = [None] * len(cond_volumes)
+    locals_: List[Optional[torch.Tensor]] = [None] * len(cond_volumes)
+
+    def finish(v):
+        lo, hi, per = bounds[v]
+        conds = cond_volumes[v]
+        n, hw = conds[0].shape[0], tuple(conds[0].shape[-2:])
+        local = locals_[v]
+        if local is None:                        # this rank owns no slice of the volume
+            local = torch.zeros(per, 1, hw[0], hw[1], device=device)
+        if world == 1 or not gather:
+            outs[v] = local[:hi - lo] if world == 1 else local
+        else:
+            full = torch.empty(world * per, 1, hw[0], hw[1], device=device)
+            dist.all_gather_into_tensor(full, local, group=group)       # the ONLY collective of the path
+            outs[v] = full[:n]
+        locals_[v] = None
+
+    nxt = prepare(items[0]) if items else None
+    done_upto = 0                                # volumes [0, done_upto) are finished (gathers stay in volume order)
+    for i, (v, b0, b1) in enumerate(items):
+        cb, x_init, latents, noises, ev = nxt
+        if ev is not None:
+            main.wait_event(ev)
         fake = sample_fn(cb, x_init, latents, noises)
-        local[b0 - lo:b1 - lo] = ((fake + 1.0) / 2.0).clamp(0.0, 1.0)
-    if world == 1 or not gather:
-        return local[:hi - lo] if world == 1 else local
-    full = torch.empty(world * per, 1, hw[0], hw[1], device=device)
-    dist.all_gather_into_tensor(full, local, group=group)           # the ONLY collective of the path
-    return full[:n]
+        lo, hi, per = bounds[v]
+        if locals_[v] is None:
+            locals_[v] = torch.zeros(per, 1, fake.shape[-2], fake.shape[-1], device=device)   # padded shard
+        locals_[v][b0 - lo:b1 - lo] = ((fake + 1.0) / 2.0).clamp(0.0, 1.0)
+        nxt = prepare(items[i + 1]) if i + 1 < len(items) else None        # overlaps the sampling just enqueued
+        last_of_volume = i + 1 == len(items) or items[i + 1][0] != v
+        if last_of_volume:
+            while done_upto <= v:                # also volumes in between of which this rank owns nothing
+                finish(done_upto)
+                done_upto += 1
+    while done_upto < len(cond_volumes):
+        finish(done_upto)
+        done_upto += 1
+    return outs
+
+
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def predict_slices_sharded(sample_fn: Callable, conds: Sequence[torch.Tensor], *, seed: int = 0, volume: int = 0,
+                           nz: int = 100, n_time: int = 4, batch: int = 64, device=None,
+                           group=None, gather: bool = True, prefetch: bool = True) -> torch.Tensor:
+    """One volume: see predict_volumes_sharded.  conds: n_cond tensors [N, 1, H, W] in [-1, 1]."""
+    return predict_volumes_sharded(sample_fn, [conds], seed=seed, first_volume=volume, nz=nz, n_time=n_time, batch=batch,
+                                   device=device, group=group, gather=gather, prefetch=prefetch)[0]
+
+
+class GraphSliceSampler:
+    """`sample_fn` for predict_slices_sharded / predict_volume backed by ONE captured CUDA graph of the whole
+    n_time-step loop at a fixed batch (sampling.GraphSampler): a shard of b <= batch slices is copied into the
+    graph's static buffers, the graph is replayed, the first b outputs are returned.  Rows b..batch-1 keep whatever
+    the previous call left there; the kernels are batch-invariant (tests), so they cannot influence rows 0..b-1.
+    Removes the ~1500 eager launches per batch from the host's critical path - what limits scaling when a volume's
+    155 slices are spread over 8 GPUs (20 slices per rank)."""
+
+    def __init__(self, coefficients, generator1, generator2, n_time, batch, size, nz, n_cond=3, device='cuda'):
+        from .sampling import GraphSampler
+        self.batch = int(batch)
+        self.gs = GraphSampler(coefficients, generator1, generator2, n_time, self.batch, size, nz, n_cond=n_cond,
+                               device=device, warmup=1)
+
+    def __call__(self, conds, x_init, latents, noises):
+        b = x_init.shape[0]
+        if b > self.batch:
+            raise RuntimeError(f"mu-diff_b200: GraphSliceSampler captured for batch {self.batch}, got {b}")
+        gs = self.gs
+        for d, s in zip(gs.conds, conds):
+            d[:b].copy_(s, non_blocking=True)
+        gs.x_init[:b].copy_(x_init, non_blocking=True)
+        for d, s in zip(gs.latents, latents):
+            d[:b].copy_(s, non_blocking=True)
+        for d, s in zip(gs.noises, noises):
+            d[:b].copy_(s, non_blocking=True)
+        return gs.replay()[:b].clone()
 
 
 def predict_volume(sample_fn: Callable, volumes: Sequence[np.ndarray], *, slice_half_range: int = 80, seed: int = 0,
@@ -128,7 +237,8 @@ def predict_volume(sample_fn: Callable, volumes: Sequence[np.ndarray], *, slice_
     for v in volumes:
         vn = robust_minmax_to_minus1_1(v)
         sl = np.ascontiguousarray(np.moveaxis(vn[:, :, s0:s1 + 1], 2, 0))[:, None]      # [n,1,H,W]
-        conds.append(torch.from_numpy(sl.astype(np.float32, copy=False)))
+        t = torch.from_numpy(sl.astype(np.float32, copy=False))
+        conds.append(t.pin_memory() if torch.device(device).type == 'cuda' else t)   # pinned: the H2D copy is truly async
     pred = predict_slices_sharded(sample_fn, conds, seed=seed, volume=volume_index, nz=nz, n_time=n_time,
                                   batch=batch, device=torch.device(device), group=group)
     return reconstruct_volume_from_slices(pred[:, 0].cpu().numpy(), shape, s0, s1)

@@ -156,3 +156,24 @@ def test_resblock_module_api_nchw_input(M):
     y = blk(x.to(DEV), temb.to(DEV), zemb.to(DEV))
     assert tuple(y.shape) == (2, 128, 8, 8)
     assert (y.cpu() - ref).abs().max().item() <= 1e-4
+
+
+def test_volume_graph_slice_sampler_matches_eager(M):
+    """volume.GraphSliceSampler (one captured graph at a fixed batch, short shards padded) == eager
+    sample_from_model on the same slices, bit for bit (batch-invariant kernels), for any shard length."""
+    from mudiff_b200 import volume as V
+    cfg = O.default_config(num_channels_dae=64, image_size=64)
+    ns, g1, g2, _, _ = _build(M, cfg, 'bf16')
+    co = M.Posterior_Coefficients(ns, DEV)
+    n = 7
+    conds, _, _, _ = O.synthetic_inputs(n, 64, cfg, seed=5)
+    conds = [c.contiguous() for c in conds]
+
+    def eager(c, x, z, e):
+        return M.sample_from_model(co, g1, c[0], g2, c[1], c[2], cfg.num_timesteps, x, None, ns, latents=z, noises=e)
+
+    ref = V.predict_slices_sharded(eager, conds, seed=3, volume=1, nz=cfg.nz, n_time=cfg.num_timesteps, batch=4, device=DEV)
+    gsamp = V.GraphSliceSampler(co, g1, g2, cfg.num_timesteps, 4, 64, cfg.nz, n_cond=3, device=DEV)
+    out = V.predict_slices_sharded(gsamp, conds, seed=3, volume=1, nz=cfg.nz, n_time=cfg.num_timesteps, batch=4, device=DEV)
+    assert tuple(out.shape) == (n, 1, 64, 64)
+    assert torch.equal(out, ref)

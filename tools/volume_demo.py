@@ -24,8 +24,9 @@ from mudiff_b200.utils import randomize_
 ap = argparse.ArgumentParser()
 ap.add_argument('--slices', type=int, default=155)
 ap.add_argument('--size', type=int, default=256)
-ap.add_argument('--batch', type=int, default=32)
+ap.add_argument('--batch', type=int, default=64)
 ap.add_argument('--volumes', type=int, default=1)
+ap.add_argument('--eager', action='store_true', help='eager launches instead of one CUDA graph per batch')
 args = ap.parse_args()
 
 world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -46,21 +47,31 @@ g2 = randomize_(M.NCSNpp_adaptive(cfg), 1).to(dev).eval()
 co = M.Posterior_Coefficients(cfg, dev)
 
 
-def sample(c, x, z, e):
+def sample_eager(c, x, z, e):
     return M.sample_from_model(co, g1, c[0], g2, c[1], c[2], 4, x, None, cfg, latents=z, noises=e)
 
 
+per_rank = (args.slices + world - 1) // world
+gbatch = V.balanced_batch(per_rank, args.batch)
+sample = sample_eager if args.eager else V.GraphSliceSampler(co, g1, g2, 4, gbatch, args.size, cfg.nz, n_cond=3, device=dev)
+
+
 gen = torch.Generator().manual_seed(42)
-conds = [torch.randn(args.slices, 1, args.size, args.size, generator=gen).clamp(-3, 3) / 3 for _ in range(3)]
+conds = [(torch.randn(args.slices, 1, args.size, args.size, generator=gen).clamp(-3, 3) / 3).pin_memory() for _ in range(3)]
+if world > 1:                                   # NCCL connects lazily: keep the one-off channel set-up out of the timed region
+    warm = torch.zeros(world * 8, device=dev)
+    dist.all_gather_into_tensor(warm, warm[:8].clone())
+    dist.barrier()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-for v in range(args.volumes):
-    full = V.predict_slices_sharded(sample, conds, seed=7, volume=v, nz=cfg.nz, n_time=4, batch=args.batch, device=dev)
+fulls = V.predict_volumes_sharded(sample, [conds] * args.volumes, seed=7, first_volume=0, nz=cfg.nz, n_time=4, batch=gbatch,
+                                  device=dev)
+full = fulls[-1]
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 h = hashlib.sha256(full.cpu().numpy().tobytes()).hexdigest()[:16]
 if rank == 0:
     print(f"VOLUME world={world} slices={args.slices} size={args.size} volumes={args.volumes}: {args.volumes * args.slices / dt:.1f} slices/s "
-          f"(eager, incl. per-slice RNG + all-gather), checksum(last volume)={h} shape={tuple(full.shape)}", flush=True)
+          f"({'eager' if args.eager else 'CUDA graph'}, batch {gbatch}, incl. per-slice RNG + all-gather), checksum(last volume)={h} shape={tuple(full.shape)}", flush=True)
 if world > 1:
     dist.destroy_process_group()
