@@ -99,6 +99,14 @@ int mudiff_posterior_update(const float* x01, int64_t x01_bstride, const float* 
  * ------------------------------------------------------------------------------- */
 int mudiff_gn_stats(const void* x, int c, int ld, int dtype, int batch, int64_t hw,
                     double* chstats, int st_ld, int st_off, void* stream);
+/* Single-pass GroupNorm (+ AdaGN gamma/beta, + SiLU) of a dense bf16 NHWC tensor: out = act(GN(x)*gamma + beta) AND the
+ * per-channel (sum, sumsq) statistics of x (same layout as mudiff_gn_stats) with ONE read of x: a persistent
+ * cooperative grid keeps every CTA's chunk of an image in shared memory between the statistics and the apply phase.
+ * MUDIFF_EUNSUPPORTED when the image is too large for the stages (callers then use gn_stats + gn_apply). */
+int mudiff_gn_fused(const void* x, void* out, int c, int batch, int64_t hw, int groups, const float* gamma,
+                    const float* beta, int64_t gb_bstride, float eps, int act, double* chstats, int st_ld,
+                    int st_off, void* stream);
+
 /* Folded GroupNorm / AdaGN parameters table[b][c] = (gamma*rstd, beta - mean*gamma*rstd) (float pairs, [batch][c0+c1])
  * from per-channel (sum, sumsq) statistics of one or two concatenated sources; consumed by mudiff_conv_tc's
  * A-operand transform (a_xform). */

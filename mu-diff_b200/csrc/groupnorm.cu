@@ -317,6 +317,215 @@ int launch_apply(const void* x0, int c0, int ld0, const void* x1, int c1, int ld
   return mudiff_launch_status();
 }
 
+// ---------------------------------------------------------------------------------
+// Single-pass GroupNorm + AdaGN + activation ("gn_fused"): statistics AND apply with ONE read of the tensor.
+// The two-kernel path reads x twice from HBM (the tensors are 0.5 - 2 GB at B = 64, far beyond the 126 MB L2).
+// Here a persistent cooperative grid (one CTA per SM) walks the images in order; CTA c owns pixel chunk c of EVERY
+// image and keeps it in shared memory between the two phases:
+//   L(b)  bulk-async copy (cp.async.bulk + mbarrier) of its chunk of image b into one of D stages
+//   S(b)  per-channel (sum, sumsq) of the chunk -> partial[b][c]; the LAST CTA to arrive for image b (ticket) adds the
+//         G partials in a fixed order, publishes chstats[b] (same [B, C, 2] doubles as gn_stats) and sets flag[b]
+//   A(a)  a = b - (D-1): wait for flag[a], fold mean / rstd / gamma / beta, apply + activation from the shared-memory
+//         copy, store; the stage is then refilled with image a + D
+// so the latency of the cross-CTA reduction (a few us) is covered by the D - 1 images in flight.  Deterministic and
+// batch-invariant: chunking depends on (HW, grid) only, all reductions have a fixed order.  The last CTA to finish
+// the launch resets the flags / tickets (CUDA-graph replays need no host-side reset).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gnf_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct GnFusedP {
+  const __nv_bfloat16* x; __nv_bfloat16* out;
+  int C, cv, groups, batch, D;
+  long long hw; int ppc;                         // pixels per chunk
+  const float* gamma; const float* beta; long long gb_bstride;
+  float eps; int act;
+  double* chstats; int st_ld, st_off;            // [B][st_ld][2]
+  double* partial;                               // [B][G][C][2]
+  unsigned int* tickets;                         // [B]
+  unsigned int* flags;                           // [B]
+  unsigned int* done;                            // [1]
+  uint32_t stage_bytes;
+};
+
+__global__ void __launch_bounds__(256, 1) gn_fused_kernel(const GnFusedP p) {
+  extern __shared__ __align__(128) uint8_t gnf_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(gnf_smem);                 // [D] mbarriers
+  float* s_part = reinterpret_cast<float*>(gnf_smem + 64);                // [lanes][C][2] cross-lane reduction
+  __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
+  __shared__ bool s_last;
+  const int C = p.C, cv = p.cv;
+  const int lanes = blockDim.x / cv;
+  uint8_t* stages = gnf_smem + 64 + ((size_t)lanes * C * 2 * sizeof(float) + 127) / 128 * 128;
+  const int G = gridDim.x, c = blockIdx.x;
+  const long long px0 = (long long)c * p.ppc;
+  long long npx = p.hw - px0; if (npx > p.ppc) npx = p.ppc; if (npx < 0) npx = 0;
+  const uint32_t bytes = (uint32_t)(npx * C * 2);
+  const int my_cv = threadIdx.x % cv, lane = threadIdx.x / cv, ch = my_cv * 8;
+  const int cpg = C / p.groups;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.D; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gnf_smem_u32(&full[i])), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue_load = [&](int b) {                 // thread 0 only
+    if (bytes == 0) return;
+    const int st = b % p.D;
+    const uint32_t bar = gnf_smem_u32(&full[st]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    const __nv_bfloat16* src = p.x + ((long long)b * p.hw + px0) * C;
+    uint8_t* dst = stages + (size_t)st * p.stage_bytes;
+    // chunks of <= 64 KB per bulk copy
+    for (uint32_t off = 0; off < bytes; off += 65536u) {
+      const uint32_t n = bytes - off < 65536u ? bytes - off : 65536u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(gnf_smem_u32(dst + off)), "l"((const uint8_t*)src + off), "r"(n), "r"(bar) : "memory");
+    }
+  };
+  if (threadIdx.x == 0)
+    for (int b = 0; b < p.D && b < p.batch; ++b) issue_load(b);
+
+  for (int b = 0; b < p.batch + p.D - 1; ++b) {
+    if (b < p.batch) {
+      // ------------------------------ S(b) ------------------------------
+      const int st = b % p.D;
+      const uint32_t parity = (uint32_t)((b / p.D) & 1);
+      if (bytes) {
+        uint32_t ok = 0; long long t0 = clock64();
+        while (!ok) {
+          asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                       : "=r"(ok) : "r"(gnf_smem_u32(&full[st])), "r"(parity) : "memory");
+          if (!ok && clock64() - t0 > 4000000000LL) __trap();
+        }
+      }
+      const uint8_t* sm = stages + (size_t)st * p.stage_bytes;
+      float sum[8], sq[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; }
+      if (lane < lanes)
+        for (long long q2 = lane; q2 < npx; q2 += lanes) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(sm + (q2 * C + ch) * 2);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h2[i]);
+            sum[2 * i] += f.x; sq[2 * i] = fmaf(f.x, f.x, sq[2 * i]);
+            sum[2 * i + 1] += f.y; sq[2 * i + 1] = fmaf(f.y, f.y, sq[2 * i + 1]);
+          }
+        }
+      __syncthreads();                           // s_part free (previous image's readers are done)
+      if (lane < lanes) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s_part[((size_t)lane * C + ch + i) * 2 + 0] = sum[i];
+          s_part[((size_t)lane * C + ch + i) * 2 + 1] = sq[i];
+        }
+      }
+      __syncthreads();
+      double* mine = p.partial + (((long long)b * G + c) * C) * 2;
+      for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        double a = 0.0;
+        for (int l = 0; l < lanes; ++l) a += (double)s_part[(size_t)l * C * 2 + i];
+        mine[i] = a;
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&p.tickets[b], 1u);
+        s_last = (t == (unsigned int)G - 1);
+      }
+      __syncthreads();
+      if (s_last) {                              // last CTA of image b: fixed-order sum of the G partials -> chstats[b]
+        __threadfence();
+        const double* pb = p.partial + (long long)b * G * C * 2;
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          int k = 0;
+          for (; k + 4 <= G; k += 4) {
+            a0 += pb[(long long)(k + 0) * C * 2 + i]; a1 += pb[(long long)(k + 1) * C * 2 + i];
+            a2 += pb[(long long)(k + 2) * C * 2 + i]; a3 += pb[(long long)(k + 3) * C * 2 + i];
+          }
+          for (; k < G; ++k) a0 += pb[(long long)k * C * 2 + i];
+          p.chstats[((long long)b * p.st_ld + p.st_off) * 2 + i] = (a0 + a1) + (a2 + a3);
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) { p.tickets[b] = 0; atomicExch(&p.flags[b], 1u); }
+      }
+    }
+    const int a = b - (p.D - 1);
+    if (a >= 0 && a < p.batch) {
+      // ------------------------------ A(a) ------------------------------
+      if (threadIdx.x == 0) {
+        long long t0 = clock64();
+        while (atomicAdd(&p.flags[a], 0u) == 0u) { if (clock64() - t0 > 4000000000LL) __trap(); }
+      }
+      __syncthreads();
+      __threadfence();
+      for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < cpg; ++i) {
+          const double* sp = p.chstats + ((long long)a * p.st_ld + p.st_off + g * cpg + i) * 2;
+          s1 += __ldcg(sp); s2 += __ldcg(sp + 1);
+        }
+        const double cnt = (double)p.hw * (double)cpg;
+        const double m = s1 / cnt;
+        double var = s2 / cnt - m * m;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = (float)m;
+        s_rstd[g] = (float)(1.0 / sqrt(var + (double)p.eps));
+      }
+      __syncthreads();
+      const int st = a % p.D;
+      if (lane < lanes && npx > 0) {
+        float sc[8], sh[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int cc = ch + k, g = cc / cpg;
+          const float ga = p.gamma ? p.gamma[(long long)a * p.gb_bstride + cc] : 1.f;
+          const float be = p.beta ? p.beta[(long long)a * p.gb_bstride + cc] : 0.f;
+          sc[k] = ga * s_rstd[g];
+          sh[k] = be - s_mean[g] * sc[k];
+        }
+        const uint8_t* sm = stages + (size_t)st * p.stage_bytes;
+        __nv_bfloat16* dst = p.out + ((long long)a * p.hw + px0) * C + ch;
+        for (long long q2 = lane; q2 < npx; q2 += lanes) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(sm + (q2 * C + ch) * 2);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h2[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float t = fmaf(v[k], sc[k], sh[k]);
+            if (p.act == MUDIFF_ACT_SILU) t = silu_f(t);
+            v[k] = t;
+          }
+          store_vec<__nv_bfloat16>(dst + q2 * C, v);
+        }
+      }
+      __syncthreads();                           // every reader of the stage is done -> refill it
+      if (threadIdx.x == 0 && a + p.D < p.batch) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads of the stage before the async refill
+        issue_load(a + p.D);
+      }
+    }
+  }
+  // the last CTA of the launch resets the flags for the next launch (graph replays)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(p.done, 1u);
+    if (t == (unsigned int)G - 1) {
+      for (int b = 0; b < p.batch; ++b) p.flags[b] = 0;
+      __threadfence();
+      *p.done = 0;
+    }
+  }
+}
+
 // Folded GroupNorm / AdaGN parameters for consumers that apply the normalisation themselves (mudiff_conv_tc's
 // A-operand transform): table[b][c] = (scale, shift) with scale = gamma * rstd, shift = beta - mean * scale.
 // One block per image, one thread per channel; same double-precision group statistics as gn_apply_kernel.
@@ -433,4 +642,80 @@ extern "C" int mudiff_gn_scale_shift(const double* st0, int st0_ld, int c0, cons
   gn_scale_shift_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(st0, st0_ld, c0, st1, st1_ld, c1, gamma, beta, gb_bstride,
                                                                    (double)hw, groups, eps, table);
   return mudiff_launch_status();
+}
+
+// Single-pass GroupNorm (+AdaGN scale/shift, +SiLU): out = act(GN(x) * gamma + beta) and chstats[b][st_off + c] = per-channel
+// (sum, sumsq) of x, with ONE read of x (gn_fused_kernel).  bf16 in/out, dense NHWC (pixel stride == c), c % 8 == 0.
+// Returns MUDIFF_EUNSUPPORTED when an image chunk does not fit the shared-memory stages (callers use gn_stats + gn_apply).
+struct GnFusedScratch { double* partial = nullptr; size_t pcap = 0; unsigned int* ctr = nullptr; int ccap = 0; };
+static GnFusedScratch g_gnf[16];
+
+extern "C" int mudiff_gn_fused(const void* x, void* out, int c, int batch, int64_t hw, int groups, const float* gamma,
+                               const float* beta, int64_t gb_bstride, float eps, int act, double* chstats, int st_ld,
+                               int st_off, void* stream) {
+  if (!x || !out || !chstats || batch <= 0 || hw <= 0 || groups <= 0 || c <= 0 || st_ld < c + st_off) return MUDIFF_EINVAL;
+  if (act != MUDIFF_ACT_NONE && act != MUDIFF_ACT_SILU) return MUDIFF_EINVAL;
+  if (c % 8 || c > GN_MAX_C || c % groups || groups > GN_MAX_C / 4 || c / 8 > 256) return MUDIFF_EUNSUPPORTED;
+  if (((uintptr_t)x % 16) || ((uintptr_t)out % 16)) return MUDIFF_EUNSUPPORTED;
+  const int cv = c / 8;
+  const int block = (256 / cv) * cv;
+  const int lanes = block / cv;
+  const size_t fixed = 64 + ((size_t)lanes * c * 2 * sizeof(float) + 127) / 128 * 128;
+  // two CTAs per SM when the stages fit (twice the latency hiding: an iteration is a chain of dependent global round
+  // trips - ticket, flag, statistics, gamma/beta), else one; three stages when they fit, else two
+  int G = 0, D = 0, ppc = 0;
+  size_t stage_bytes = 0;
+  for (int R = 1; R >= 1 && !G; --R) {     // R = 2 (two CTAs per SM) measured slower: more partials, same dependent chain
+    const size_t budget = R == 2 ? 108 * 1024 : 200 * 1024;
+    const int g = MUDIFF_NUM_SMS * R;
+    const int pp = (int)((hw + g - 1) / g);
+    const size_t sb = ((size_t)pp * c * 2 + 127) / 128 * 128;
+    for (int d = 3; d >= 2; --d)
+      if (fixed + (size_t)d * sb <= budget) { G = g; D = d; ppc = pp; stage_bytes = sb; break; }
+  }
+  if (!G) return MUDIFF_EUNSUPPORTED;
+  if (batch < D) D = batch < 1 ? 1 : batch;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
+  GnFusedScratch& sc = g_gnf[dev];
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  const size_t need = (size_t)batch * G * c * 2;      // G <= 2 * MUDIFF_NUM_SMS
+  if (need > sc.pcap) {
+    if (cs != cudaStreamCaptureStatusNone) return MUDIFF_EUNSUPPORTED;     // must be sized by a warm-up run
+    double* pnew = nullptr;
+    if (cudaMalloc(&pnew, need * 2 * sizeof(double)) != cudaSuccess) return (int)cudaGetLastError();
+    sc.partial = pnew; sc.pcap = need * 2;
+  }
+  if (2 * batch + 1 > sc.ccap) {
+    if (cs != cudaStreamCaptureStatusNone) return MUDIFF_EUNSUPPORTED;
+    const int cap = 2 * batch + 1 < 4096 ? 4096 : 2 * (2 * batch + 1);
+    unsigned int* t = nullptr;
+    if (cudaMalloc(&t, cap * sizeof(unsigned int)) != cudaSuccess) return (int)cudaGetLastError();
+    cudaMemset(t, 0, cap * sizeof(unsigned int));
+    sc.ctr = t; sc.ccap = cap;
+  }
+  static bool attr_set[16] = {};
+  if (!attr_set[dev]) {
+    if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) != cudaSuccess)
+      return (int)cudaGetLastError();
+    attr_set[dev] = true;
+  }
+  GnFusedP p;
+  p.x = (const __nv_bfloat16*)x; p.out = (__nv_bfloat16*)out;
+  p.C = c; p.cv = cv; p.groups = groups; p.batch = batch; p.D = D; p.hw = hw; p.ppc = ppc;
+  p.gamma = gamma; p.beta = beta; p.gb_bstride = gb_bstride; p.eps = eps; p.act = act;
+  p.chstats = chstats; p.st_ld = st_ld; p.st_off = st_off;
+  p.partial = sc.partial;
+  const int half = sc.ccap / 2;
+  p.tickets = sc.ctr; p.flags = sc.ctr + half; p.done = sc.ctr + sc.ccap - 1;
+  p.stage_bytes = (uint32_t)stage_bytes;
+  const size_t smem = fixed + (size_t)D * stage_bytes;
+  void* args[] = {(void*)&p};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)gn_fused_kernel, dim3(G), dim3(block), args, smem, st);
+  ++g_mudiff_launches;
+  if (e == cudaErrorCooperativeLaunchTooLarge) { cudaGetLastError(); return MUDIFF_EUNSUPPORTED; }
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  return 0;
 }

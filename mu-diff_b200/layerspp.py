@@ -71,8 +71,8 @@ class AdaptiveGroupNorm(nn.Module):
         L.require_cuda(*srcs)
         gb = self.style_params(style) if gb is None else gb
         c = self.in_channel
-        return ops.gn_apply(srcs, [ops.get_chstats(t) for t in srcs], self.num_groups, gamma=gb, beta=gb[:, c:],
-                            gb_bstride=gb.stride(0), eps=self.norm.eps, act=act)
+        return ops.gn_apply_auto(srcs, self.num_groups, gamma=gb, beta=gb[:, c:], gb_bstride=gb.stride(0),
+                                 eps=self.norm.eps, act=act)
 
 
 class GroupNorm_Conv(nn.Module):

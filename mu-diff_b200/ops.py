@@ -224,8 +224,50 @@ def gn_scale_shift(srcs, chstats, groups, gamma=None, beta=None, gb_bstride=0, e
     return table
 
 
+# Single-pass GroupNorm (statistics + apply with ONE read of the tensor, persistent cooperative kernel, mudiff_gn_fused).
+# Correct and tested, but NOT a win on B200 so far: every image costs each CTA a chain of dependent global round trips
+# (partial write -> ticket -> cross-CTA reduce -> flag -> statistics -> gamma/beta) that three shared-memory stages do
+# not cover: 0.87 ms per launch against 0.30 ms for gn_stats + gn_apply at B = 64, C = 64, 256^2
+# (profiles/r01_single_pass_gn.md).  MUDIFF_GN_SINGLE_PASS=1 turns it on.
+GN_SINGLE_PASS = _os.environ.get('MUDIFF_GN_SINGLE_PASS', '0') != '0'
+
+
+def gn_single_pass(x, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_NONE):
+    """act(GN(x)*gamma + beta) AND x's per-channel statistics (attached like get_chstats) from ONE read of x.
+    Returns None when the kernel does not take the shape (image chunk too large for the shared-memory stages,
+    non-dense or non-bf16 tensor): the caller then runs gn_stats + gn_apply."""
+    if not GN_SINGLE_PASS or x.dtype != torch.bfloat16:
+        return None
+    b, c, h, w = x.shape
+    if _pix_ld(x) != c or c % 8:
+        return None
+    cs = torch.empty((b, c, 2), dtype=torch.float64, device=x.device)
+    out = empty_nhwc(b, c, h, w, x.dtype, x.device)
+    rc = L.lib().mudiff_gn_fused(x.data_ptr(), out.data_ptr(), c, b, h * w, groups,
+                                 gamma.data_ptr() if gamma is not None else None,
+                                 beta.data_ptr() if beta is not None else None, gb_bstride, float(eps), act,
+                                 cs.data_ptr(), c, 0, L.stream_ptr(x.device))
+    if rc == L.EUNSUPPORTED:
+        return None
+    L.check(rc, 'gn_fused')
+    set_chstats(x, cs)
+    return out
+
+
+def gn_apply_auto(srcs, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_NONE):
+    """GroupNorm (+AdaGN, +act) of one tensor or the channel-concat of two: single-pass kernel when the statistics
+    of a lone source are not known yet, else statistics (cached per tensor) + apply."""
+    if len(srcs) == 1 and getattr(srcs[0], _CHSTATS, None) is None:
+        y = gn_single_pass(srcs[0], groups, gamma, beta, gb_bstride, eps, act)
+        if y is not None:
+            return y
+    return gn_apply(srcs, [get_chstats(t) for t in srcs], groups, gamma=gamma, beta=beta, gb_bstride=gb_bstride, eps=eps, act=act)
+
+
 def group_norm(srcs, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_NONE, out_dtype=None):
     srcs = [s if is_nhwc_view(s) else as_nhwc(s) for s in srcs]
+    if out_dtype is None or out_dtype == srcs[0].dtype:
+        return gn_apply_auto(srcs, groups, gamma, beta, gb_bstride, eps, act)
     return gn_apply(srcs, [get_chstats(s) for s in srcs], groups, gamma, beta, gb_bstride, eps, act, out_dtype)
 
 
@@ -361,9 +403,11 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
                 cs = buf[:, off:off + n]
             L.check(L.lib().mudiff_stats_finalize(partial.data_ptr(), tpi, n, buf.data_ptr(), buf.shape[1], off, b, st),
                     'stats_finalize')
-        else:
+        elif stats_out is not None or not (GN_SINGLE_PASS and region is out):
             cs = gn_stats(region, out=stats_out)
-        if region is out:
+        else:
+            cs = None                    # lazy: the consuming GroupNorm computes them (single-pass kernel or get_chstats)
+        if region is out and cs is not None:
             set_chstats(out, cs)
     return out
 

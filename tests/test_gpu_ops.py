@@ -139,6 +139,41 @@ def test_groupnorm_adagn_silu(M, dtype, c0, c1):
     np.testing.assert_allclose(y.float().cpu().numpy(), ref.numpy(), rtol=0, atol=tol)
 
 
+@pytest.mark.parametrize('shape', [(5, 64, 64, 64), (3, 384, 32, 32), (4, 64, 256, 256), (2, 256, 128, 128), (70, 128, 16, 16)])
+@pytest.mark.parametrize('adagn', [False, True])
+def test_groupnorm_single_pass(M, shape, adagn):
+    """mudiff_gn_fused (statistics + AdaGN + SiLU from ONE read, cooperative grid) == F.group_norm reference and ==
+    the two-kernel path; exported statistics == per-channel sums; repeated launches (flag / ticket reset) identical."""
+    from mudiff_b200 import ops
+    torch.manual_seed(8)
+    b, c, h, w = shape
+    groups = min(c // 4, 32)
+    x = ops.as_nhwc((torch.randn(b, c, h, w, device='cuda') * 1.5 + 0.4).to(torch.bfloat16))
+    gb = torch.cat([1 + 0.2 * torch.randn(b, c), 0.3 * torch.randn(b, c)], dim=1).cuda() if adagn else None
+    kw = dict(gamma=gb, beta=gb[:, c:], gb_bstride=2 * c) if adagn else {}
+    ops.GN_SINGLE_PASS = True                     # independent of the MUDIFF_GN_SINGLE_PASS default
+    y = ops.gn_single_pass(x, groups, act=1, **kw)
+    assert y is not None, "shape should be supported by the single-pass kernel"
+    cs = ops.get_chstats(x)
+    ref = F.group_norm(x.float(), groups, eps=1e-6)
+    if adagn:
+        ref = ref * gb[:, :c, None, None] + gb[:, c:, None, None]
+    ref = F.silu(ref)
+    assert (y.float() - ref).abs().max().item() <= 6e-2
+    x64 = x.double()
+    np.testing.assert_allclose(cs[..., 0].cpu().numpy(), x64.sum(dim=(2, 3)).cpu().numpy(), rtol=1e-6, atol=1e-3)
+    np.testing.assert_allclose(cs[..., 1].cpu().numpy(), (x64 ** 2).sum(dim=(2, 3)).cpu().numpy(), rtol=1e-6, atol=1e-3)
+    # two-kernel path on the same tensor (statistics of the stand-alone pass, then apply)
+    x2 = x.clone()
+    y2 = ops.gn_apply([x2], [ops.gn_stats(x2)], groups, act=1, **kw)
+    assert (y.float() - y2.float()).abs().max().item() <= 4e-2            # stats differ in the last bits only
+    for _ in range(3):                                                      # flags / tickets reset by the kernel itself
+        x3 = x.clone()
+        y3 = ops.gn_single_pass(x3, groups, act=1, **kw)
+        assert torch.equal(y3, y)
+        assert torch.equal(ops.get_chstats(x3), cs)
+
+
 # ------------------------------------------------------------------ convolution --
 def _conv_ref(segs, ws, pad1=True):
     out = 0
