@@ -204,6 +204,22 @@ int mudiff_conv_tc_query(const mudiff_conv_desc* d, int32_t* out);
  * out[b] = softmax(Q[b] K[b]^T * scale) V[b].  qk [B, L, 2C] bf16 (q | k per token), vt = V^T [B, C, L] bf16,
  * out [B, L, C] bf16.  C == 256, L % 128 == 0, else MUDIFF_EUNSUPPORTED (callers use the unfused kernels). */
 int mudiff_attention_tc(const void* qk, const void* vt, void* out, int batch, int L, int C, float scale, void* stream);
+/* -------------------------------------------------------------------------------
+ * Volume prediction front / back end (engine/test_volume.py:135-191, 269-294).
+ * mudiff_volume_window: exact robust [pmin, pmax] percentile window over the voxels != 0 of a fp32 volume
+ * (np.percentile 'linear' semantics, fall back to min / max, degenerate -> all-zero output), kept on the device inside
+ * `workspace` (mudiff_volume_workspace_bytes() bytes).  mudiff_volume_to_slices: out [n,1,sh,sw] = the normalised
+ * ([-1, 1]) axial slices s0..s0+n-1 of vol [H, W, Z], bilinear-resized (align_corners = False) when (sh, sw) != (H, W).
+ * mudiff_slices_to_volume: vol [H, W, Z] = zeros with slices s0.. = pred [n,1,H,W] (mapped (x+1)/2, clamped, if to01).
+ * mudiff_volume_window_read: device float[3] <- lo, hi, status(int bits) of the window in `workspace`.
+ * ------------------------------------------------------------------------------- */
+int mudiff_volume_workspace_bytes(void);
+int mudiff_volume_window(const float* vol, int64_t n, float pmin, float pmax, void* workspace, void* stream);
+int mudiff_volume_window_read(const void* workspace, float* window, void* stream);
+int mudiff_volume_to_slices(const float* vol, int h, int w, int z, int s0, int n, int sh, int sw,
+                            const void* workspace, float* out, void* stream);
+int mudiff_slices_to_volume(const float* pred, int h, int w, int z, int s0, int n, int to01, float* vol, void* stream);
+
 /* Debug: out[0..7] = (timed_out, block, warp, lane, barrier smem address, parity, grid, 0) of the last mbarrier
  * wait that hit its 4e9-cycle bound inside mudiff_conv_tc (kept in mapped host memory). */
 int mudiff_debug_last_timeout(int32_t* out);

@@ -57,6 +57,11 @@ PROTOTYPES = {
     'mudiff_conv_tc': [C.POINTER(ConvDesc), _P],
     'mudiff_conv_tc_query': [C.POINTER(ConvDesc), C.POINTER(C.c_int32)],
     'mudiff_attention_tc': [_P, _P, _P, _I, _I, _I, _F, _P],
+    'mudiff_volume_workspace_bytes': [],
+    'mudiff_volume_window': [_P, _L, _F, _F, _P, _P],
+    'mudiff_volume_window_read': [_P, _P, _P],
+    'mudiff_volume_to_slices': [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    'mudiff_slices_to_volume': [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     'mudiff_debug_last_timeout': [C.POINTER(C.c_int32)],
     'mudiff_debug_dump': [C.POINTER(C.c_int32), _I],
     'mudiff_debug_selftest': [],

@@ -21,36 +21,74 @@ import torch
 import torch.distributed as dist
 
 
-# ---- host-side pre/post processing (engine/test_volume.py:135-181) ------------------
-def robust_minmax_to_minus1_1(vol: np.ndarray, mask: Optional[np.ndarray] = None, pmin: float = 1.0,
-                              pmax: float = 99.0) -> np.ndarray:
-    """[pmin, pmax] percentile window over non-zero voxels -> [-1, 1] (test_volume.py:135-157)."""
-    data = vol.astype(np.float32, copy=False)
-    m = (data != 0) if mask is None else (mask.astype(bool) & (data == data))
-    if not np.any(m):
-        return np.zeros_like(data, dtype=np.float32)
-    vals = data[m]
-    lo, hi = np.percentile(vals, pmin), np.percentile(vals, pmax)
-    if not np.isfinite(lo) or not np.isfinite(hi) or hi <= lo:
-        lo, hi = float(vals.min()), float(vals.max())
-        if hi <= lo:
-            return np.zeros_like(data, dtype=np.float32)
-    return np.clip((data - lo) / (hi - lo), 0.0, 1.0) * 2.0 - 1.0
-
-
+# ---- pre/post processing on the GPU (engine/test_volume.py:135-181, 270-276, 285) -------------------
+# The numpy restatement of these functions lives in oracle/volume_oracle.py (test infrastructure).
 def center_slice_bounds(depth: int, half_range: int) -> Tuple[int, int]:
     """Inclusive [start, end] of the centre +-half_range axial slices (test_volume.py:159-168)."""
     c = depth // 2
     return max(0, c - half_range), min(depth - 1, c + half_range)
 
 
-def reconstruct_volume_from_slices(pred: np.ndarray, original_shape, start_slice: int, end_slice: int) -> np.ndarray:
-    """pred [n, H, W] -> zeros(original_shape) with slices start..end filled (test_volume.py:170-181)."""
-    vol = np.zeros(original_shape, dtype=np.float32)
-    for i in range(pred.shape[0]):
-        k = start_slice + i
-        if start_slice <= k <= end_slice and k < original_shape[2]:
-            vol[:, :, k] = pred[i]
+def _require_cuda_device(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError("mu-diff_b200: volume pre/post-processing runs on the GPU only (no CPU path; the numpy "
+                           "restatement is test infrastructure in oracle/volume_oracle.py)")
+    return device
+
+
+def volume_window(vol_dev: torch.Tensor, pmin: float = 1.0, pmax: float = 99.0) -> torch.Tensor:
+    """Robust percentile window of a device volume (fp32): returns the opaque device workspace holding (lo, hi, status)
+    for volume_to_slices.  Exact order statistics by a two-level radix select (mudiff_volume_window)."""
+    from . import _lib as L
+    lib = L.lib()
+    ws = torch.empty(lib.mudiff_volume_workspace_bytes(), dtype=torch.uint8, device=vol_dev.device)
+    L.check(lib.mudiff_volume_window(vol_dev.data_ptr(), vol_dev.numel(), float(pmin), float(pmax), ws.data_ptr(),
+                                     L.stream_ptr(vol_dev.device)), 'volume_window')
+    return ws
+
+
+def window_values(ws: torch.Tensor) -> Tuple[float, float, int]:
+    """(lo, hi, status) of a volume_window workspace (synchronises; for tests / logging)."""
+    from . import _lib as L
+    out = torch.empty(3, dtype=torch.float32, device=ws.device)
+    L.check(L.lib().mudiff_volume_window_read(ws.data_ptr(), out.data_ptr(), L.stream_ptr(ws.device)), 'volume_window_read')
+    lo, hi = out[:2].tolist()
+    return lo, hi, int(out[2:].view(torch.int32).item())
+
+
+def volume_to_slices(volume: np.ndarray, half_range: int, image_size: int, device='cuda', pmin: float = 1.0,
+                     pmax: float = 99.0) -> Tuple[torch.Tensor, int, int]:
+    """load_and_preprocess_volume + per-slice tensors (test_volume.py:183-192, 270-276) as two kernels: volume [H, W, Z]
+    (any float dtype; cast to fp32 like :142) -> normalised [-1, 1] conditioning slices [n, 1, S, S] on `device`."""
+    from . import _lib as L
+    device = _require_cuda_device(device)
+    h, w, z = volume.shape
+    s0, s1 = center_slice_bounds(z, half_range)
+    n = s1 - s0 + 1
+    host = torch.from_numpy(np.ascontiguousarray(volume, dtype=np.float32))
+    vol_dev = host.to(device, non_blocking=True)
+    ws = volume_window(vol_dev, pmin, pmax)
+    out = torch.empty((n, 1, image_size, image_size), dtype=torch.float32, device=device)
+    L.check(L.lib().mudiff_volume_to_slices(vol_dev.data_ptr(), h, w, z, s0, n, image_size, image_size, ws.data_ptr(),
+                                            out.data_ptr(), L.stream_ptr(device)), 'volume_to_slices')
+    return out, s0, s1
+
+
+def slices_to_volume(pred: torch.Tensor, original_shape, start_slice: int, to01: bool = False) -> torch.Tensor:
+    """reconstruct_volume_from_slices (test_volume.py:170-181) on the device: pred [n, 1, H, W] -> [H, W, Z] fp32 with the
+    other slices zero; `to01` also applies the ((x + 1) / 2).clamp(0, 1) of :285."""
+    from . import _lib as L
+    _require_cuda_device(pred.device)
+    h, w, z = (int(v) for v in original_shape)
+    n = pred.shape[0]
+    if tuple(pred.shape[-2:]) != (h, w):
+        # the reference's `vol[:, :, k] = sl` raises for mismatching shapes, too
+        raise ValueError(f"could not broadcast input array from shape {tuple(pred.shape[-2:])} into shape {(h, w)}")
+    pred = pred.float().contiguous()
+    vol = torch.empty((h, w, z), dtype=torch.float32, device=pred.device)
+    L.check(L.lib().mudiff_slices_to_volume(pred.data_ptr(), h, w, z, start_slice, n, 1 if to01 else 0, vol.data_ptr(),
+                                            L.stream_ptr(pred.device)), 'slices_to_volume')
     return vol
 
 
@@ -225,20 +263,20 @@ class GraphSliceSampler:
 
 def predict_volume(sample_fn: Callable, volumes: Sequence[np.ndarray], *, slice_half_range: int = 80, seed: int = 0,
                    volume_index: int = 0, nz: int = 100, n_time: int = 4, batch: int = 64, device='cuda',
-                   group=None) -> np.ndarray:
-    """engine/test_volume.py:209-299 without the NIfTI I/O: normalise each input modality volume
-    [H, W, Z], take the centre slices, sample them (sharded + batched), rebuild the [H, W, Z] volume."""
+                   group=None, image_size: Optional[int] = None) -> np.ndarray:
+    """engine/test_volume.py:209-299 without the NIfTI I/O: normalise each input modality volume [H, W, Z] (robust
+    percentile window, on the GPU), take the centre slices (bilinear resize to `image_size` if given and different),
+    sample them (sharded + batched), rebuild the [H, W, Z] volume on the GPU and return it as numpy."""
+    device = _require_cuda_device(device)
     shape = volumes[0].shape
     for v in volumes:
         if v.shape != shape:
             raise ValueError(f"All input volumes must share shape. Got {v.shape} vs {shape}")
-    s0, s1 = center_slice_bounds(shape[2], slice_half_range)
-    conds = []
+    size = int(image_size) if image_size else int(shape[0])
+    conds, s0 = [], 0
     for v in volumes:
-        vn = robust_minmax_to_minus1_1(v)
-        sl = np.ascontiguousarray(np.moveaxis(vn[:, :, s0:s1 + 1], 2, 0))[:, None]      # [n,1,H,W]
-        t = torch.from_numpy(sl.astype(np.float32, copy=False))
-        conds.append(t.pin_memory() if torch.device(device).type == 'cuda' else t)   # pinned: the H2D copy is truly async
+        c, s0, _ = volume_to_slices(v, slice_half_range, size, device)
+        conds.append(c)
     pred = predict_slices_sharded(sample_fn, conds, seed=seed, volume=volume_index, nz=nz, n_time=n_time,
-                                  batch=batch, device=torch.device(device), group=group)
-    return reconstruct_volume_from_slices(pred[:, 0].cpu().numpy(), shape, s0, s1)
+                                  batch=batch, device=device, group=group)      # already in [0, 1]
+    return slices_to_volume(pred, shape, s0).cpu().numpy()

@@ -177,3 +177,25 @@ def test_volume_graph_slice_sampler_matches_eager(M):
     out = V.predict_slices_sharded(gsamp, conds, seed=3, volume=1, nz=cfg.nz, n_time=cfg.num_timesteps, batch=4, device=DEV)
     assert tuple(out.shape) == (n, 1, 64, 64)
     assert torch.equal(out, ref)
+
+
+def test_predict_volume_gpu_pipeline_vs_oracle(M):
+    """volume.predict_volume (GPU percentile window + slicing, sharded sampling, GPU re-stack) == the oracle pipeline
+    (numpy pre/post of engine/test_volume.py + the same sampler) for a deterministic stand-in sampler."""
+    from mudiff_b200 import volume as V
+    from oracle import volume_oracle as VO
+    rng = np.random.default_rng(11)
+    vols = [np.where(rng.random((32, 32, 13)) < 0.3, 0.0, np.round(rng.gamma(2.0, 90.0, (32, 32, 13)))) for _ in range(3)]
+
+    def sampler(c, x, z, e):                     # any deterministic function of the conditioning slices and the noise
+        return torch.tanh(0.5 * c[0] - 0.25 * c[1] + 0.1 * c[2] + 0.05 * x)
+
+    out = V.predict_volume(sampler, vols, slice_half_range=4, seed=5, volume_index=2, nz=10, n_time=4, batch=4, device=DEV)
+    conds = [VO.preprocess_volume(v, 4, 32) for v in vols]
+    s0, s1 = conds[0][1], conds[0][2]
+    cs = [c[0].to(DEV) for c in conds]
+    n = cs[0].shape[0]
+    x_init, lat, noi = V.draw_slice_noise(5, 2, list(range(n)), (32, 32), 10, 4, torch.device(DEV))
+    ref = VO.reconstruct_volume_from_slices(list(VO.postprocess_slices(sampler(cs, x_init, lat, noi))), vols[0].shape, s0, s1)
+    assert out.shape == vols[0].shape and out.dtype == np.float32
+    np.testing.assert_array_equal(out, ref)

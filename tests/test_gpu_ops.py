@@ -494,3 +494,55 @@ def test_small_dense_and_embeddings(M):
     z = torch.randn(4, 100)
     np.testing.assert_allclose(ops.pixelnorm(z.cuda()).cpu().numpy(),
                                (z / torch.sqrt(torch.mean(z ** 2, dim=1, keepdim=True) + 1e-8)).numpy(), atol=1e-6)
+
+
+# ------------------------------------------------------------------ volume pre/post --
+@pytest.mark.parametrize('name', ['mri', 'smooth', 'flat', 'zeros', 'two_values'])
+def test_volume_pre_post_gpu_vs_reference_golden(M, golden_dir, name):
+    """GPU front / back end of volume prediction (percentile window by radix select, normalise + slice + resize,
+    clamp + re-stack) against the outputs of the reference's own functions (tests/golden/volume.npz).
+    Bit-exact except through the bilinear resize (ATen's CPU kernel may contract differently): 2e-6 there."""
+    from mudiff_b200 import volume as V
+    g = _npz(golden_dir, 'volume.npz')
+    vol = g[f'{name}_vol']
+    half, size, s0, s1 = (int(v) for v in g[f'{name}_p'])
+    conds, a, b = V.volume_to_slices(vol, half, size, device='cuda')
+    assert (a, b) == (s0, s1)
+    ref = g[f'{name}_conds']
+    assert tuple(conds.shape) == ref.shape
+    if size == vol.shape[0] and size == vol.shape[1]:
+        np.testing.assert_array_equal(conds.cpu().numpy(), ref)
+    else:
+        np.testing.assert_allclose(conds.cpu().numpy(), ref, rtol=0, atol=2e-6)
+    # the window itself == np.percentile on the non-zero voxels (fp32, 'linear')
+    data = vol.astype(np.float32)
+    vals = data[data != 0]
+    ws = V.volume_window(torch.from_numpy(data).cuda())
+    lo, hi, status = V.window_values(ws)
+    if vals.size and np.percentile(vals, 99.0) > np.percentile(vals, 1.0):
+        assert status == 0
+        assert np.float32(lo) == np.percentile(vals, 1.0) and np.float32(hi) == np.percentile(vals, 99.0)
+    else:
+        assert status == 1
+    # back end: ((fake + 1) / 2).clamp(0, 1) + re-stack
+    fake = torch.from_numpy(g[f'{name}_fake']).cuda()
+    rebuilt = V.slices_to_volume(fake, vol.shape, s0, to01=True)
+    np.testing.assert_array_equal(rebuilt.cpu().numpy(), g[f'{name}_rebuilt'])
+
+
+def test_volume_window_large_random(M):
+    """Exact order statistics on a BraTS-sized volume (240 x 240 x 155) with heavy ties and a zero background."""
+    from mudiff_b200 import volume as V
+    rng = np.random.default_rng(3)
+    vol = np.where(rng.random((240, 240, 155)) < 0.6, 0.0, np.round(rng.gamma(2.0, 200.0, (240, 240, 155)))).astype(np.float32)
+    vals = vol[vol != 0]
+    for pmin, pmax in ((1.0, 99.0), (0.5, 99.5), (25.0, 75.0)):
+        ws = V.volume_window(torch.from_numpy(vol).cuda(), pmin, pmax)
+        lo, hi, status = V.window_values(ws)
+        assert status == 0
+        assert np.float32(lo) == np.percentile(vals, pmin) and np.float32(hi) == np.percentile(vals, pmax)
+    # continuous values: interpolated percentiles
+    vol2 = rng.normal(100.0, 30.0, (64, 64, 40)).astype(np.float32)
+    ws = V.volume_window(torch.from_numpy(vol2).cuda())
+    lo, hi, status = V.window_values(ws)
+    assert np.float32(lo) == np.percentile(vol2[vol2 != 0], 1.0) and np.float32(hi) == np.percentile(vol2[vol2 != 0], 99.0)

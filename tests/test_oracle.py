@@ -103,3 +103,19 @@ def test_sampling_loop_matches_reference(golden_dir):
     conds, x_init, latents, noises = O.synthetic_inputs(2, 32, cfg, seed=42)
     x = O.sample_from_model(O.PosteriorCoefficients(cfg), sd1, sd2, cfg, conds, x_init, latents, noises)
     np.testing.assert_allclose(x.numpy(), g['nf64_s32_sample'], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize('name', ['mri', 'smooth', 'flat', 'zeros', 'two_values'])
+def test_volume_oracle_matches_reference_golden(golden_dir, name):
+    """oracle/volume_oracle.py == outputs of the reference's own engine/test_volume.py functions
+    (tests/golden/make_volume_golden.py ran them), bit for bit."""
+    from oracle import volume_oracle as VO
+    g = np.load(os.path.join(golden_dir, 'volume.npz'))
+    vol = g[f'{name}_vol']
+    half, size, s0, s1 = (int(v) for v in g[f'{name}_p'])
+    np.testing.assert_array_equal(VO.robust_minmax_to_minus1_1(vol), g[f'{name}_norm'])
+    conds, a, b = VO.preprocess_volume(vol, half, size)
+    assert (a, b) == (s0, s1)
+    np.testing.assert_array_equal(conds.numpy(), g[f'{name}_conds'])
+    pred = VO.postprocess_slices(torch.from_numpy(g[f'{name}_fake']))
+    np.testing.assert_array_equal(VO.reconstruct_volume_from_slices(list(pred), vol.shape, s0, s1), g[f'{name}_rebuilt'])

@@ -60,19 +60,24 @@ def test_shard_bounds_cover_exactly():
             assert seen == list(range(n))
 
 
-def test_volume_pre_post_processing():
+def test_volume_oracle_pre_post_processing():
+    """The numpy restatement of engine/test_volume.py:135-181 (oracle/volume_oracle.py) and the index helpers."""
     import mudiff_b200.volume as V
+    from oracle import volume_oracle as VO
     rng = np.random.default_rng(0)
     vol = rng.random((8, 8, 21)).astype(np.float32) * 100
     vol[0, 0, :] = 0
-    x = V.robust_minmax_to_minus1_1(vol)
+    x = VO.robust_minmax_to_minus1_1(vol)
     assert x.min() >= -1 and x.max() <= 1 and x.dtype == np.float32
     vals = vol[vol != 0]
     lo, hi = np.percentile(vals, 1), np.percentile(vals, 99)
     np.testing.assert_allclose(x, np.clip((vol - lo) / (hi - lo), 0, 1) * 2 - 1, atol=1e-6)
-    assert V.robust_minmax_to_minus1_1(np.zeros((2, 2, 2))).sum() == 0
+    assert VO.robust_minmax_to_minus1_1(np.zeros((2, 2, 2))).sum() == 0
     assert V.center_slice_bounds(155, 80) == (0, 154)
     assert V.center_slice_bounds(200, 80) == (20, 180)
-    out = V.predict_volume(_fake_sampler, [vol, vol * 0.5, vol + 1], slice_half_range=5, nz=10, batch=4, device='cpu')
-    assert out.shape == vol.shape
-    assert np.all(out[:, :, :5] == 0) and np.all(out[:, :, 16:] == 0) and out[:, :, 5:16].max() > 0
+    sl, s0, s1 = VO.extract_center_slices(vol, 5)
+    assert (s0, s1) == V.center_slice_bounds(21, 5) == (5, 15) and len(sl) == 11
+    out = VO.reconstruct_volume_from_slices([np.ones((8, 8))] * 11, vol.shape, s0, s1)
+    assert np.all(out[:, :, :5] == 0) and np.all(out[:, :, 16:] == 0) and np.all(out[:, :, 5:16] == 1)
+    with pytest.raises(RuntimeError):                     # the product pre/post-processing has no CPU path
+        V.predict_volume(_fake_sampler, [vol, vol, vol], slice_half_range=5, nz=10, batch=4, device='cpu')
