@@ -283,6 +283,60 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
   }
 }
 
+// stride-2 VALID variant of the stem kernel (Cin == 1, pad 0): the 3x3 stride-2 conv of the input-pyramid branch
+// (conv_downsample_2d, up_or_down_sampling.py:183) after its FIR pre-filter.  One output pixel x 8 channels per
+// thread, all nine taps in bounds by construction, channel pairs on FFMA2.
+template <typename TO>
+__global__ void __launch_bounds__(256) conv_stem_s2_kernel(SimtP p) {
+  const int nv = p.n / 8;
+  const int n0 = (threadIdx.x % nv) * 8;
+  const int lane = threadIdx.x / nv, lanes = blockDim.x / nv;
+  if (lane >= lanes) return;
+  const float* wt = (const float*)p.wt;
+  f32x2 w2[9][4], bs2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = n0 + 2 * j;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w2[t][j] = pack2(wt[c * 9 + t], wt[(c + 1) * 9 + t]);
+    bs2[j] = pack2(p.bias ? p.bias[c] : 0.f, p.bias ? p.bias[c + 1] : 0.f);
+  }
+  const int ld = p.a_ld[0];
+  const int W = p.w, H = p.h, WO = p.wo, HO = p.ho;
+  const int64_t rows = (int64_t)p.batch * HO;
+  for (int64_t row = (int64_t)blockIdx.x * STEM_ROWS; row < rows && row < (int64_t)(blockIdx.x + 1) * STEM_ROWS; ++row) {
+    const int b = (int)(row / HO), y = (int)(row - (int64_t)b * HO);
+    const float* in = (const float*)p.a[0] + ((int64_t)b * H + 2 * y) * W * ld;
+    for (int x = lane; x < WO; x += lanes) {
+      float v[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) v[t] = __ldg(in + ((int64_t)(t / 3) * W + 2 * x + t % 3) * ld);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f32x2 a = bs2[j];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) a = fma2(pack2(v[t], v[t]), w2[t][j], a);
+        unpack2(a, acc[2 * j], acc[2 * j + 1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float r = acc[j] + (p.rowbias ? p.rowbias[(int64_t)b * p.rowbias_ld + n0 + j] : 0.f);
+        acc[j] = apply_act(r * p.alpha, p.act);
+      }
+      const int64_t pix = row * WO + x;
+      TO* op = (TO*)p.out + pix * p.out_ld + p.out_coff + n0;
+      if constexpr (sizeof(TO) == 2) {
+        store_vec<TO>(op, acc);
+      } else {
+        float lo[4] = {acc[0], acc[1], acc[2], acc[3]}, hi[4] = {acc[4], acc[5], acc[6], acc[7]};
+        store_vec<float>((float*)op, lo);
+        store_vec<float>((float*)op + 4, hi);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // Fused stem: conv3x3(1 -> N) -> GroupNorm / AdaGN -> SiLU without ever storing the raw conv output
 // (ConvFeatBlock / ConvBlock / ConvBlock_GAP, backbones/layerspp.py:394-501).  The GroupNorm statistics of a
@@ -610,6 +664,18 @@ int launch_simt(const SimtP& p, cudaStream_t st) {
       int block = (256 / nv) * nv;
       conv_stem_kernel<TO><<<(unsigned)((rows + STEM_ROWS - 1) / STEM_ROWS), block, 0, st>>>(p);
       return mudiff_launch_status();
+    }
+  }
+  if constexpr (sizeof(TA) == 4) {
+    if (plain && p.stride == 2 && p.pad == 0 && p.nseg == 1 && p.a_taps[0] == 9 && p.a_c[0] == 1 && p.n % 8 == 0 && p.n <= 256 &&
+        !p.residual && (p.out_ld % 8 == 0) && (p.out_coff % 8 == 0) && p.ho > 0 && p.wo > 0) {
+      const int nv = p.n / 8;
+      const int block = (256 / nv) * nv;
+      const int64_t orows = (int64_t)p.batch * p.ho;
+      if (orows < (1LL << 31)) {
+        conv_stem_s2_kernel<TO><<<(unsigned)((orows + STEM_ROWS - 1) / STEM_ROWS), block, 0, st>>>(p);
+        return mudiff_launch_status();
+      }
     }
   }
   if (plain && s1 && p.n == 1 && p.a_c[0] % 64 == 0 && p.a_c[0] <= 512 && p.a_ld[0] % (16 / (int)sizeof(TA)) == 0 &&

@@ -206,6 +206,22 @@ def test_conv_simt_stride2_valid(M):
     np.testing.assert_allclose(y.cpu().numpy(), ref.numpy(), rtol=0, atol=2e-5)
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_conv_stem_stride2_valid(M, dtype):
+    """1 -> 64 stride-2 VALID 3x3 conv of the input-pyramid branch (conv_downsample_2d, up_or_down_sampling.py:183)."""
+    from mudiff_b200 import ops
+    torch.manual_seed(12)
+    x = torch.randn(3, 1, 35, 41)
+    wgt = torch.randn(64, 1, 3, 3) / 3
+    bias = torch.randn(64)
+    ref = F.conv2d(x, wgt, bias, stride=2, padding=0)
+    y = ops.conv([(ops.as_nhwc(x.cuda()), 9)], ops.pack_conv_weight(wgt.cuda(), (1,), torch.float32), 64, bias=bias.cuda(),
+                 stride=2, pad=0, force='simt', out_dtype=dtype)
+    assert tuple(y.shape) == tuple(ref.shape)
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    np.testing.assert_allclose(y.float().cpu().numpy(), ref.numpy(), rtol=0, atol=tol)
+
+
 TC_CASES = {
     # flags: 2 = no halo staging, 8 = no stationary weights, 16 = one pixel tile per unit
     'gemm_1x1':       dict(B=2, H=32, W=32, C=[64], taps=[1], N=64, flags=0),
