@@ -1,21 +1,25 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a  (bf16 x bf16 -> fp32), version 2.
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a  (bf16 x bf16 -> fp32), version 3.
 //
 //   D[128 pixels, n_tile] += A[128 pixels, 64 ch] * W[n_tile, 64 ch]^T        per (tap, channel block)
 //
-// Persistent, warp-specialised CTA (224 threads, one per SM), each CTA owns a CONTIGUOUS range of
-// work units (unit = MT consecutive 128-pixel tiles of one image x one N tile):
-//   warp 0      TMA producer for the A ring: NHWC activation boxes through a 4-D tensor map (conv
-//               padding = TMA out-of-bounds zero fill).  3x3 segments are staged as ONE halo box
-//               {64ch, tw+2, th+2} per channel block; the nine taps are nine UMMA descriptors into
-//               that tile (start address shifted by whole 128-byte pixel rows, SBO = halo row pitch).
-//   warp 1      TMA producer for the B ring: K-major weight sub-tiles {64, n_tile} through a 3-D map,
+// Persistent, warp-specialised CTA (256 threads; 384 with the operand transform), one per SM; each CTA owns a
+// CONTIGUOUS range of work units (unit = MT consecutive 128-pixel tiles of one image x one N tile):
+//   warp 0      TMA producer of the A rings (one ring per MMA-issuing warp): NHWC activation boxes through a 4-D
+//               tensor map (conv padding = TMA out-of-bounds zero fill).  3x3 segments are staged as ONE halo box
+//               {64ch, tw+2, th+2} per channel block; the nine taps are nine UMMA descriptors into that tile (start
+//               address shifted by whole 128-byte pixel rows, SBO = halo row pitch).
+//   warp 1      TMA producer of the B ring: K-major weight sub-tiles {64, n_tile} through a 3-D map,
 //               or - when all of K x n_tile fits - ONE stationary load of the whole weight matrix.
-//   warp 2      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x n_tile x 16); one weight
-//               sub-tile feeds the MMAs of all MT pixel tiles before it is released (tcgen05.commit).
-//   warps 3-6   epilogue: tcgen05.ld -> bias / temb row-bias / alpha / residual / activation ->
-//               bf16|fp32 NHWC stores, plus optional per-tile per-channel (sum, sum^2) partials for
+//   warps 2, 3  TMEM allocator (warp 2) + the two single-thread tcgen05.mma issuers (UMMA 128 x n_tile x 16): warp 2
+//               owns pixel tile 0 of every unit and its accumulator, warp 3 tile 1 (idle when MT == 1); a weight
+//               sub-tile is released when both have committed (tcgen05.commit).
+//   warps 4-7   epilogue, one per TMEM lane quadrant: tcgen05.ld -> bias / temb row-bias / alpha / residual /
+//               activation -> bf16|fp32 NHWC stores, plus optional per-tile per-channel (sum, sum^2) partials for
 //               the GroupNorm that consumes the output (butterfly shuffles, no atomics -> deterministic).
+//   warps 8-11  (only with a_xform) GroupNorm/AdaGN scale + shift + SiLU applied to the staged A tile in shared
+//               memory between its TMA load and its MMAs.
 // TMEM holds acc_stages x MT accumulators so that unit i+1's MMAs overlap unit i's epilogue.
+// Every mbarrier has exactly ONE in-order waiter role, and every wait is bounded (deadlock dump + trap).
 #include <cuda.h>
 #include <string.h>
 #include "common.cuh"
@@ -778,8 +782,8 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   const uint32_t avail = kSmemMax - fixed;
   const uint32_t b_total = (uint32_t)(ktot / 64) * p.b_sub_bytes;
   // A ring depth: two groups of tiles for halo staging; plain 16 KB tiles (GEMM mode, 1x1 segments only)
-  // get four groups - a 2-slot ring of plain tiles faulted intermittently on B200 in epilogue-bound GEMMs
-  // (N = 4096, K = 256; root cause not understood), and the extra 32 KB are free there.
+  // get four groups (16 KB tiles: the extra depth is free there, and epilogue-bound GEMMs such as N = 4096, K = 256
+  // need it to keep the loads ahead of the MMAs).
   // With the A-operand transform a tile spends an extra ~0.5 us between its TMA load and its MMAs: the A rings
   // must be three to four tiles deep per issuing warp (measured: two-deep rings made the fused launches 60 %
   // slower, three-deep 13 %), so stationary weights are only taken when they leave that much room.
