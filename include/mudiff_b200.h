@@ -190,6 +190,8 @@ int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream);
  * conv3x3(1 -> n) -> GroupNorm / AdaGN -> SiLU with the raw conv output never stored.  The GroupNorm statistics
  * follow from second moments of the 1-channel input: mudiff_stem_moments writes double[batch][54]
  * (9 patch sums + 45 patch products), mudiff_stem_conv_gn_act consumes them. */
+int mudiff_stem_conv_tc(const float* x, const float* wt, const float* bias, const float* scale_shift, int act,
+                        void* out, int out_ld, int out_coff, int out_dtype, int batch, int h, int w, int n, void* stream);
 int mudiff_stem_moments(const float* x, int ld, int batch, int h, int w, double* moments, void* stream);
 int mudiff_stem_conv_gn_act(const float* x, int ld, const float* wt, const float* bias, const double* moments,
                             const float* gamma, const float* beta, int64_t gb_bstride, int groups, float eps,

@@ -66,6 +66,7 @@ PROTOTYPES = {
     'mudiff_debug_dump': [C.POINTER(C.c_int32), _I],
     'mudiff_debug_selftest': [],
     'mudiff_conv_simt': [C.POINTER(ConvDesc), _I, _P],
+    'mudiff_stem_conv_tc': [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'mudiff_stem_moments': [_P, _I, _I, _I, _I, _P, _P],
     'mudiff_stem_conv_gn_act': [_P, _I, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'mudiff_softmax_rows': [_P, _P, _I, _L, _I, _F, _P],

@@ -3,6 +3,7 @@
 // fp32 products, which tcgen05 does not offer), and (2) the path for shapes the
 // tensor-core kernel does not take: Cin=1 stem convs, the Cout=1 head conv, the
 // stride-2 input-pyramid conv.  Same mudiff_conv_desc contract as mudiff_conv_tc.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -802,6 +803,14 @@ extern "C" int mudiff_stem_conv_gn_act(const float* x, int ld, const float* wt, 
                                                  (double)h * (double)w, scale_shift);
   int rc = mudiff_launch_status();
   if (rc) return rc;
+  // tensor-core stem (stem_tc.cuh): correct, but measured SLOWER than the CUDA-core kernel below (355 vs 308 us per
+  // launch at B = 64, 256^2: its 128-thread epilogue is the bottleneck), so it is opt-in: MUDIFF_STEM_TC=1
+  static int use_tc = -1;
+  if (use_tc < 0) { const char* e = getenv("MUDIFF_STEM_TC"); use_tc = (e && e[0] == '1') ? 1 : 0; }
+  if (use_tc && ld == 1 && n % 32 == 0 && out_dtype == MUDIFF_BF16) {      // the fp32 parity path stays on exact fp32 FMAs
+    rc = mudiff_stem_conv_tc(x, wt, bias, scale_shift, act, out, out_ld, out_coff, out_dtype, batch, h, w, n, stream);
+    if (rc != MUDIFF_EUNSUPPORTED) return rc;
+  }
   SimtP p;
   memset(&p, 0, sizeof(p));
   p.a[0] = x; p.a_c[0] = 1; p.a_ld[0] = ld; p.a_taps[0] = 9; p.nseg = 1; p.a_batched = 1;

@@ -852,6 +852,7 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
 }
 
 #include "attn_tc.cuh"
+#include "stem_tc.cuh"
 
 }  // namespace
 
@@ -900,6 +901,39 @@ extern "C" int mudiff_conv_tc_query(const mudiff_conv_desc* d, int32_t* out) {
   out[0] = p.tile_h; out[1] = p.tile_w; out[2] = p.tpi; out[3] = p.n_tile; out[4] = p.MT;
   out[5] = p.stationary; out[6] = p.a_slots; out[7] = p.b_slots; out[8] = p.acc_stages; out[9] = p.seg_halo[0];
   return 0;
+}
+
+// Stem conv3x3(1 -> n) (+ folded GroupNorm/AdaGN scale-shift, + activation) on the tensor cores, see stem_tc.cuh.
+// x fp32 [B, H, W] dense; wt fp32 [n][9]; scale_shift fp32 [B][n][2] or NULL; out NHWC bf16 / fp32.
+extern "C" int mudiff_stem_conv_tc(const float* x, const float* wt, const float* bias, const float* scale_shift, int act,
+                                   void* out, int out_ld, int out_coff, int out_dtype, int batch, int h, int w, int n,
+                                   void* stream) {
+  if (!x || !wt || !out || batch <= 0 || h <= 0 || w <= 0 || n <= 0) return MUDIFF_EINVAL;
+  if (n % 32 || n > 256 || out_ld % 8 || out_coff % 8 || ((uintptr_t)out % 16)) return MUDIFF_EUNSUPPORTED;
+  if (act != MUDIFF_ACT_NONE && act != MUDIFF_ACT_SILU) return MUDIFF_EUNSUPPORTED;
+  if (out_dtype != MUDIFF_BF16 && out_dtype != MUDIFF_F32) return MUDIFF_EUNSUPPORTED;
+  ensure_dbg();
+  StemTcP p;
+  p.x = x; p.H = h; p.W = w; p.batch = batch; p.wt = wt; p.bias = bias; p.scale_shift = scale_shift; p.N = n; p.act = act;
+  p.out = out; p.out_ld = out_ld; p.out_coff = out_coff;
+  p.tiles_per_image = (int)(((long long)h * w + 127) / 128);
+  p.total_units = (long long)batch * p.tiles_per_image;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+  static bool attr_set[16][2] = {};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
+  const int which = out_dtype == MUDIFF_F32 ? 1 : 0;
+  if (!attr_set[dev][which]) {
+    cudaError_t e = which ? cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmem)
+                          : cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev][which] = true;
+  }
+  const int grid = (int)(p.total_units < MUDIFF_NUM_SMS ? p.total_units : MUDIFF_NUM_SMS);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (which) stem_tc_kernel<true><<<grid, 288, kStemSmem, st>>>(p);
+  else stem_tc_kernel<false><<<grid, 288, kStemSmem, st>>>(p);
+  return mudiff_launch_status();
 }
 
 // Fused attention O = softmax(Q K^T * scale) V (AttnBlockpp, backbones/layerspp.py:118-122), see attn_tc.cuh.

@@ -512,6 +512,31 @@ def test_small_dense_and_embeddings(M):
                                (z / torch.sqrt(torch.mean(z ** 2, dim=1, keepdim=True) + 1e-8)).numpy(), atol=1e-6)
 
 
+def test_stem_conv_tensor_core_kernel(M):
+    """mudiff_stem_conv_tc (im2col + split-bf16 UMMA, stem_tc.cuh) == conv3x3(1 -> N) * scale + shift -> SiLU in fp32;
+    fp32 output so that only the split-bf16 residue remains (dropped lo*lo products and the bf16 rounding of the lo
+    parts: <= 9 taps * |x||w| * 2^-17 ~ 1e-4 for |x| ~ 3): 2e-4 absolute.
+    Ragged image (pixel tiles crossing rows and the last, partial tile) and N in {32, 64, 128}."""
+    import ctypes as C
+    from mudiff_b200 import ops, _lib as L
+    torch.manual_seed(13)
+    for (B, H, W, N) in [(3, 37, 29, 64), (2, 64, 64, 128), (5, 16, 24, 32)]:
+        x = (torch.randn(B, 1, H, W) * 0.8).cuda()
+        wgt = (torch.randn(N, 1, 3, 3) / 3).cuda()
+        bias = (torch.randn(N) * 0.2).cuda()
+        ss = torch.stack([1 + 0.3 * torch.randn(B, N), 0.4 * torch.randn(B, N)], dim=-1).cuda().contiguous()
+        ssd = ss.double().cpu()                      # fp64 CPU reference (cuDNN would use TF32 here)
+        ref = F.conv2d(x.double().cpu(), wgt.double().cpu(), bias.double().cpu(), padding=1) * ssd[:, :, 0, None, None] + ssd[:, :, 1, None, None]
+        ref = F.silu(ref).float().cuda()
+        out = ops.empty_nhwc(B, N, H, W, torch.float32, 'cuda')
+        w9 = ops.pack_conv_weight(wgt, (1,), torch.float32)
+        rc = L.lib().mudiff_stem_conv_tc(x.data_ptr(), w9.data_ptr(), bias.data_ptr(), ss.data_ptr(), 1, out.data_ptr(),
+                                         N, 0, 0, B, H, W, N, L.stream_ptr(x.device))
+        L.check(rc, 'stem_conv_tc')
+        torch.cuda.synchronize()
+        assert (out - ref).abs().max().item() <= 2e-4, (B, H, W, N)
+
+
 # ------------------------------------------------------------------ volume pre/post --
 @pytest.mark.parametrize('name', ['mri', 'smooth', 'flat', 'zeros', 'two_values'])
 def test_volume_pre_post_gpu_vs_reference_golden(M, golden_dir, name):
