@@ -81,3 +81,51 @@ def test_volume_oracle_pre_post_processing():
     assert np.all(out[:, :, :5] == 0) and np.all(out[:, :, 16:] == 0) and np.all(out[:, :, 5:16] == 1)
     with pytest.raises(RuntimeError):                     # the product pre/post-processing has no CPU path
         V.predict_volume(_fake_sampler, [vol, vol, vol], slice_half_range=5, nz=10, batch=4, device='cpu')
+
+
+def _make_volumes(sizes):
+    g = torch.Generator().manual_seed(9)
+    return [[torch.rand(n, 1, 8, 8, generator=g) * 2 - 1 for _ in range(3)] for n in sizes]
+
+
+def _worker_multi(rank, world, port, sizes, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import mudiff_b200.volume as V
+    outs = V.predict_volumes_sharded(_fake_sampler, _make_volumes(sizes), seed=11, first_volume=4, nz=10, n_time=4, batch=3,
+                                     device='cpu')
+    for v, o in enumerate(outs):
+        np.save(os.path.join(out_dir, f'r{rank}_v{v}.npy'), o.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_multi_volume_sharded_equals_single_process(tmp_path):
+    """predict_volumes_sharded: several volumes of different depth (one shorter than the world size, so a rank owns
+    nothing of it) walked as one pipelined work list, one all-gather per volume, identical to the unsharded result
+    and to per-volume predict_slices_sharded calls."""
+    import mudiff_b200.volume as V
+    sizes = [7, 1, 10]
+    vols = _make_volumes(sizes)
+    ref = V.predict_volumes_sharded(_fake_sampler, vols, seed=11, first_volume=4, nz=10, n_time=4, batch=4, device='cpu')
+    for v, (c, r) in enumerate(zip(vols, ref)):
+        one = V.predict_slices_sharded(_fake_sampler, c, seed=11, volume=4 + v, nz=10, n_time=4, batch=2, device='cpu')
+        np.testing.assert_array_equal(r.numpy(), one.numpy())
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_multi, args=(2, port, sizes, str(tmp_path)), nprocs=2, join=True)
+    for v, r in enumerate(ref):
+        a, b = np.load(tmp_path / f'r0_v{v}.npy'), np.load(tmp_path / f'r1_v{v}.npy')
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, r.numpy())
+
+
+def test_balanced_batch():
+    import mudiff_b200.volume as V
+    assert V.balanced_batch(155, 64) == 52 and V.balanced_batch(78, 64) == 39 and V.balanced_batch(20, 64) == 20
+    assert V.balanced_batch(64, 64) == 64 and V.balanced_batch(65, 64) == 33 and V.balanced_batch(0, 64) == 1
+    for n in range(1, 400):
+        b = V.balanced_batch(n, 64)
+        k = -(-n // b)
+        assert b <= 64 and k == -(-n // 64) and k * b - n < k       # same number of batches, < 1 padded row per batch
