@@ -16,7 +16,6 @@ backbones/ncsnpp_generator_adagn_feat.py:56-277 (NCSNpp) and :454-692 (NCSNpp_ad
 """
 import functools
 
-import numpy as np
 import torch
 from torch import nn
 

@@ -2,7 +2,6 @@
 ddpm_conv1x1 / ddpm_conv3x3 factories (:104-129), get_timestep_embedding (:465-479),
 NIN (:496-505).  Convs are `Conv2d` modules with nn.Conv2d-compatible parameters
 (`weight [Cout,Cin,k,k]`, `bias [Cout]`) whose forward runs the libmudiff_b200 kernels."""
-import math
 
 import numpy as np
 import torch

@@ -13,7 +13,6 @@ which cannot be reproduced under sharding; here every slice has its own stream s
 
 NIfTI I/O (nibabel) is outside the hot path: volumes are numpy / torch arrays [H, W, Z].
 """
-import math
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
