@@ -222,6 +222,15 @@ int mudiff_volume_to_slices(const float* vol, int h, int w, int z, int s0, int n
                             const void* workspace, float* out, void* stream);
 int mudiff_slices_to_volume(const float* pred, int h, int w, int z, int s0, int n, int to01, float* vol, void* stream);
 
+/* Slice-test driver helpers (engine/test.py:265-400, dataset/dataset_brats.py:73-92):
+ * mudiff_zscore_to_unit: out = clamp(in, -3, 3) / 3.  mudiff_minmax_keys: exact global min / max (order-preserving
+ * uint32 keys, device uint32[2]; accumulate != 0 folds another tensor in).  mudiff_scale_to_u8: the reference's
+ * np.clip((x - gmin) / (gmax - gmin) * 255, 0, 255).astype(uint8) with that window ([0, 1] if constant). */
+int mudiff_zscore_to_unit(const float* in, float* out, int64_t n, void* stream);
+int mudiff_minmax_keys(const float* x, int64_t n, int accumulate, unsigned int* keys, void* stream);
+int mudiff_minmax_read(const unsigned int* keys, float* window, void* stream);
+int mudiff_scale_to_u8(const float* x, int64_t n, const unsigned int* keys, unsigned char* out, void* stream);
+
 /* Debug: out[0..7] = (timed_out, block, warp, lane, barrier smem address, parity, grid, 0) of the last mbarrier
  * wait that hit its 4e9-cycle bound inside mudiff_conv_tc (kept in mapped host memory). */
 int mudiff_debug_last_timeout(int32_t* out);

@@ -62,6 +62,10 @@ PROTOTYPES = {
     'mudiff_volume_window_read': [_P, _P, _P],
     'mudiff_volume_to_slices': [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     'mudiff_slices_to_volume': [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    'mudiff_zscore_to_unit': [_P, _P, _L, _P],
+    'mudiff_minmax_keys': [_P, _L, _I, _P, _P],
+    'mudiff_minmax_read': [_P, _P, _P],
+    'mudiff_scale_to_u8': [_P, _L, _P, _P, _P],
     'mudiff_debug_last_timeout': [C.POINTER(C.c_int32)],
     'mudiff_debug_dump': [C.POINTER(C.c_int32), _I],
     'mudiff_debug_selftest': [],

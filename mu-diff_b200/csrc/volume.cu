@@ -269,3 +269,82 @@ extern "C" int mudiff_slices_to_volume(const float* pred, int h, int w, int z, i
   restack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(pred, h, w, z, s0, n, to01, vol);
   return mudiff_launch_status();
 }
+
+// ---------------------------------------------------------------------------------
+// Slice-test driver helpers (engine/test.py:265-400, dataset/dataset_brats.py:73-92):
+//   z-score slices -> [-1, 1]   (clamp(x, -3, 3) / 3),
+//   global min / max over predictions and ground truth, and the [0, 255] uint8 export with that global window.
+// ---------------------------------------------------------------------------------
+namespace {
+
+__global__ void zscore_unit_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __fdiv_rn(fminf(fmaxf(in[i], -3.0f), 3.0f), 3.0f);
+}
+
+__global__ void minmax_init_kernel(unsigned int* keys) { keys[0] = 0xFFFFFFFFu; keys[1] = 0u; }
+__global__ void minmax_read_kernel(const unsigned int* keys, float* w) { w[0] = key2f(keys[0]); w[1] = key2f(keys[1]); }
+
+// exact and order-independent: min / max on the order-preserving integer keys
+__global__ void minmax_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ keys) {
+  unsigned int lo = 0xFFFFFFFFu, hi = 0u;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned int k = f2key(x[i]);
+    lo = min(lo, k); hi = max(hi, k);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&keys[0], lo); atomicMax(&keys[1], hi); }
+}
+
+// engine/test.py:378-388: np.clip((x - gmin) / (gmax - gmin) * 255.0, 0, 255).astype(np.uint8) with python-float gmin /
+// gmax (fp64 difference, then fp32 array arithmetic); constant images fall back to the window [0, 1] (:373-374)
+__global__ void to_u8_kernel(const float* __restrict__ x, long long n, const unsigned int* __restrict__ keys,
+                             unsigned char* __restrict__ out) {
+  float gmin = key2f(keys[0]), gmax = key2f(keys[1]);
+  if (!(gmax > gmin)) { gmin = 0.0f; gmax = 1.0f; }
+  const float den = (float)((double)gmax - (double)gmin);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = __fmul_rn(__fdiv_rn(__fsub_rn(x[i], gmin), den), 255.0f);
+    v = fminf(fmaxf(v, 0.0f), 255.0f);
+    out[i] = (unsigned char)v;                   // truncation, like ndarray.astype(np.uint8) on [0, 255]
+  }
+}
+
+}  // namespace
+
+// out = clamp(in, -3, 3) / 3  (dataset/dataset_brats.py:83,91), fp32, n elements; in == out allowed
+extern "C" int mudiff_zscore_to_unit(const float* in, float* out, int64_t n, void* stream) {
+  if (!in || !out || n < 0) return MUDIFF_EINVAL;
+  if (n == 0) return 0;
+  zscore_unit_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  return mudiff_launch_status();
+}
+
+// keys[0..1] (device uint32[2]) <- order-preserving keys of min / max over x (n > 0).  `accumulate` != 0 folds x into
+// the keys already there (global window over several tensors: predictions and ground truth, engine/test.py:368-371).
+extern "C" int mudiff_minmax_keys(const float* x, int64_t n, int accumulate, unsigned int* keys, void* stream) {
+  if (!x || !keys || n <= 0) return MUDIFF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) { minmax_init_kernel<<<1, 1, 0, st>>>(keys); ++g_mudiff_launches; }
+  minmax_kernel<<<grid_for(n, 256, MUDIFF_NUM_SMS * 8), 256, 0, st>>>(x, n, keys);
+  return mudiff_launch_status();
+}
+
+// window[0..1] (device float[2]) <- min, max decoded from the keys
+extern "C" int mudiff_minmax_read(const unsigned int* keys, float* window, void* stream) {
+  if (!keys || !window) return MUDIFF_EINVAL;
+  minmax_read_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(keys, window);
+  return mudiff_launch_status();
+}
+
+// out (uint8, n) <- the reference's global-window 8-bit export of x with the window in `keys`
+extern "C" int mudiff_scale_to_u8(const float* x, int64_t n, const unsigned int* keys, unsigned char* out, void* stream) {
+  if (!x || !keys || !out || n < 0) return MUDIFF_EINVAL;
+  if (n == 0) return 0;
+  to_u8_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, keys, out);
+  return mudiff_launch_status();
+}

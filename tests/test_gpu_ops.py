@@ -587,3 +587,48 @@ def test_volume_window_large_random(M):
     ws = V.volume_window(torch.from_numpy(vol2).cuda())
     lo, hi, status = V.window_values(ws)
     assert np.float32(lo) == np.percentile(vol2[vol2 != 0], 1.0) and np.float32(hi) == np.percentile(vol2[vol2 != 0], 99.0)
+
+
+# ------------------------------------------------------------------ slice-test driver --
+def test_testset_driver_kernels_vs_oracle(M, tmp_path):
+    """dataset normalisation, exact global window and the 8-bit export (engine/test.py:366-388) on the GPU == the
+    reference's numpy / torch expressions (oracle/testset_oracle.py), bit for bit; batched driver end to end."""
+    from mudiff_b200 import testset as T
+    from oracle import testset_oracle as TO
+    rng = np.random.default_rng(21)
+    z = (rng.normal(0.0, 1.6, (9, 24, 20))).astype(np.float32)
+    np.testing.assert_array_equal(T.zscore_to_unit(torch.from_numpy(z).cuda()).cpu().numpy(), TO.zscore_to_unit(z).numpy())
+    pred = torch.tanh(torch.from_numpy(rng.normal(0, 1.0, (9, 1, 24, 20)).astype(np.float32)))
+    gt = TO.zscore_to_unit(z).view(9, 1, 24, 20)
+    p8, g8, (lo, hi) = T.export_uint8(pred.cuda(), gt.cuda())
+    rp, rg, (rlo, rhi) = TO.export_uint8(list(pred[:, 0].numpy()), list(gt[:, 0].numpy()))
+    assert (np.float32(lo), np.float32(hi)) == (np.float32(rlo), np.float32(rhi))
+    np.testing.assert_array_equal(p8, rp)
+    np.testing.assert_array_equal(g8, rg)
+    # constant images: window falls back to [0, 1]
+    c = torch.full((2, 1, 4, 4), 0.25)
+    p8c, _, _ = T.export_uint8(c.cuda(), c.cuda())
+    rpc, _, _ = TO.export_uint8(list(c[:, 0].numpy()), list(c[:, 0].numpy()))
+    np.testing.assert_array_equal(p8c, rpc)
+    # batched driver: .npy split on disk -> predictions / ground truth -> PNGs
+    split = tmp_path / 'test'
+    split.mkdir()
+    mods = {m: rng.normal(0, 1.2, (7, 16, 16)).astype(np.float32) for m in ('FLAIR', 'T2', 'T1', 'T1CE')}
+    for m, a in mods.items():
+        np.save(split / f'{m}.npy', a)
+    arrays = T.load_split(str(tmp_path), 'test', 'T1CE')
+    assert [a.shape for a in arrays] == [(7, 16, 16)] * 4
+
+    def sampler(cb, x, zl, e):
+        return torch.tanh(0.6 * cb[0] - 0.3 * cb[1] + 0.2 * cb[2] + 0.05 * x)
+
+    pr, g = T.sample_test_split(sampler, arrays, batch=3, seed=1, nz=10, device='cuda')
+    assert tuple(pr.shape) == (7, 1, 16, 16)
+    np.testing.assert_array_equal(g[:, 0].cpu().numpy(), TO.zscore_to_unit(mods['T1CE']).numpy())
+    pr2, _ = T.sample_test_split(sampler, arrays, batch=7, seed=1, nz=10, device='cuda')
+    assert torch.equal(pr, pr2)                           # independent of the batch size (per-slice RNG streams)
+    p8, g8, _ = T.export_uint8(pr, g)
+    T.save_pngs(p8, g8, str(tmp_path / 'out'))
+    from PIL import Image
+    back = np.array(Image.open(tmp_path / 'out' / 'pred' / 'pred_00003.png'))
+    np.testing.assert_array_equal(back, p8[3])
