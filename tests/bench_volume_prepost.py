@@ -1,4 +1,5 @@
-"""Times the volume-prediction front / back end (robust percentile normalisation + centre slices + resize, clamp +
+"""(Lives under tests/ because it executes the oracle: only tests/, smoke() and bench.py's CPU-baseline leg may.)
+Times the volume-prediction front / back end (robust percentile normalisation + centre slices + resize, clamp +
 re-stack) for one BraTS-sized case (3 modalities, 240 x 240 x 155 -> 155 slices of 256^2): numpy/ATen restatement of the
 reference on the host cores vs the GPU kernels (including the H2D copy of the raw volumes and the D2H of the result)."""
 import os, sys, time
