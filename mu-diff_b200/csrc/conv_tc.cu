@@ -807,11 +807,14 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
       if (MT == 2) return MUDIFF_EUNSUPPORTED;
       return MUDIFF_EUNSUPPORTED;
     }
-    if (bs > 12) {                      // spend the surplus on a deeper A ring
-      int extra = (int)(((uint32_t)(bs - 12) * p.b_sub_bytes) / p.a_slot_bytes);
+    // 8 weight sub-tiles in flight are enough to cover the TMA latency and leave room for a third A tile per issuing
+    // warp (+2 % on the streaming N = 64 launches, tools/bcap_ab.sh); flag 1024 restores the older 12
+    const int b_cap = (d->flags & 1024) ? 12 : 8;
+    if (bs > b_cap) {                   // spend the surplus on a deeper A ring
+      int extra = (int)(((uint32_t)(bs - b_cap) * p.b_sub_bytes) / p.a_slot_bytes);
       p.a_slots += extra; if (p.a_slots > 8) p.a_slots = 8;
       p.a_slots -= p.a_slots % MT;
-      bs = 12;
+      bs = b_cap;
     }
     p.b_slots = bs;
     p.off_b = (uint32_t)p.a_slots * p.a_slot_bytes;

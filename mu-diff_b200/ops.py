@@ -16,6 +16,7 @@ SQRT2_INV = 1.0 / math.sqrt(2.0)
 import os as _os
 _ENV_FLAGS = 2 if _os.environ.get('MUDIFF_HALO', '1') == '0' else 0     # debug knob: forbid halo staging
 _ENV_FLAGS |= int(_os.environ.get('MUDIFF_XF_DBG', '0')) << 20        # timing ablations of the operand transform
+_ENV_FLAGS |= 1024 if _os.environ.get('MUDIFF_BCAP12', '0') == '1' else 0   # ablation: the older, larger B ring (12 sub-tiles)
 
 # Fused epilogue statistics (conv_tc butterfly reduction) are implemented and tested, but since the MMA issue
 # loop got fast they cost more than the stand-alone HBM-bound statistics pass for every N <= 256 (measured,
