@@ -8,7 +8,9 @@ package at the repository root.  Layout mirrors the reference for the path only:
     layers.py, dense_layer.py, layerspp.py       backbones/*
     ncsnpp_generator_adagn_feat[_healthy].py     NCSNpp, NCSNpp_adaptive
     sampling.py              engine/test.py:48-199 (+ GraphSampler)
-    volume.py                engine/test_volume.py:135-181,269-294 (sharded, batched)
+    volume.py                engine/test_volume.py:135-181,269-294 (sharded, batched, GPU pre/post)
+    testset.py               engine/test.py:265-400 (batched slice-test driver, uint8 export)
+    validation.py            engine/train.py:1148-1175 (validation sampling on weights shared with training)
     csrc/, libmudiff_b200.so C ABI (include/mudiff_b200.h)
 """
 from . import _lib, ops  # noqa: F401

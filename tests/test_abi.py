@@ -106,3 +106,35 @@ def test_fir_setup_kernel(M):
     import numpy as np
     from oracle import mudiff_oracle as O
     np.testing.assert_array_equal(M.up_or_down_sampling._setup_kernel([1, 3, 3, 1]), O.setup_kernel([1, 3, 3, 1]))
+
+
+def test_validation_share_weights_aliases_training_parameters():
+    """the fast generators alias the training modules' parameters (no copy), also through a DDP-like
+    `.module` wrapper; an in-place optimiser-style update is visible and bumps the version the pack cache keys on."""
+    import torch
+    from torch import nn
+    import mudiff_b200 as M
+    from mudiff_b200 import validation as VAL
+    from oracle import mudiff_oracle as O
+    from argparse import Namespace
+    cfg = O.default_config(num_channels_dae=16, image_size=32)
+    ns = Namespace(**vars(cfg), b200_precision='bf16')
+    train_g = M.NCSNpp(ns)                        # stands in for the reference module: same state_dict keys (tested above)
+    fast_g = M.NCSNpp(ns)
+
+    class Wrapper(nn.Module):                     # what DistributedDataParallel looks like from outside
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+
+    VAL.share_weights(fast_g, Wrapper(train_g))
+    tp, fp = dict(train_g.named_parameters()), dict(fast_g.named_parameters())
+    assert tp.keys() == fp.keys()
+    assert all(tp[k].data_ptr() == fp[k].data_ptr() for k in tp)
+    assert not any(p.requires_grad for p in fast_g.parameters()) and not fast_g.training
+    sig0 = VAL.params_signature((fast_g,))
+    with torch.no_grad():
+        next(iter(tp.values())).add_(1.0)         # optimiser step on the training module
+    k0 = next(iter(tp))
+    assert torch.equal(tp[k0], fp[k0])
+    assert VAL.params_signature((fast_g,)) != sig0

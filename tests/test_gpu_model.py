@@ -230,3 +230,31 @@ def test_full_size_256_bf16_and_fp32_vs_oracle(M):
         xg = gs.run(c, x_init.to(DEV), _to(latents), _to(noises))
         torch.cuda.synchronize()
         assert torch.equal(xg, x3)                                # graph replay == eager, bit for bit
+
+
+def test_validation_sampler_follows_weight_updates(M):
+    """validation.ValidationSampler: the fast modules alias the training modules' weights; after an in-place update
+    (an optimiser step) the sampler re-captures its graph and its output equals an eager run with the new weights."""
+    from mudiff_b200 import validation as VAL
+    cfg = O.default_config(num_channels_dae=64, image_size=32)
+    ns, tg1, tg2, _, _ = _build(M, cfg, 'bf16')                      # the "training" modules
+    mod = M.ncsnpp_generator_adagn_feat
+    f1, f2 = mod.NCSNpp(ns).to(DEV), mod.NCSNpp_adaptive(ns).to(DEV)
+    VAL.share_weights(f1, tg1)
+    VAL.share_weights(f2, tg2)
+    vs = VAL.ValidationSampler(ns, f1, f2, batch=2, size=32, n_cond=3, device=DEV)
+    conds, x_init, latents, noises = O.synthetic_inputs(2, 32, cfg, seed=3)
+    c = _to(conds)
+
+    def eager():
+        return M.sample_from_model(vs.co, tg1, c[0], tg2, c[1], c[2], cfg.num_timesteps, x_init.to(DEV), None, ns,
+                                   latents=_to(latents), noises=_to(noises))
+
+    a = vs.sample(c, x_init.to(DEV), _to(latents), _to(noises))
+    assert torch.equal(a, eager())
+    with torch.no_grad():
+        for p in tg1.parameters():
+            p.mul_(1.01)
+    b = vs.sample(c, x_init.to(DEV), _to(latents), _to(noises))
+    assert torch.equal(b, eager())
+    assert not torch.equal(a, b)
