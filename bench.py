@@ -16,8 +16,14 @@ Prints ONE JSON line (rank 0).  Keys: see the driver contract; additionally
                  bounded sample (1 slice of the same workload)
   e2e          : same metric through the public API with pinned-host inputs -> H2D -> device RNG ->
                  graph replay -> D2H of the synthesized slices, every step.
-`--impl reference` times the reference's own CPU implementation of the path (oracle port; the
-reference is Python and cannot travel to the GPU box) on all host threads.
+  volume       : BASELINE configs[2] shape through volume.predict_volumes_sharded: 8 volumes x 155 axial slices x 256^2,
+                 slices sharded over the N ranks, one CUDA graph per rank at the balanced shard batch, ONE NCCL
+                 all-gather per volume (the path's only collective); slices/s = all slices / max-over-ranks time
+  reference_gpu: (N = 1) the UNMODIFIED reference (baseline/_ref, its own loop + CUDA extensions, eager, fp16 autocast
+                 as engine/test.py:191) timed on the same GPU at B=1 and B=64 - the north star's ">= 25x" denominator
+`--impl reference` times the reference's own CPU implementation of the path on all host threads: the UNMODIFIED
+reference modules from baseline/_ref (CPU tensors -> upfirdn2d_native; `kind: "reference"`), or the oracle port of it
+when baseline/_ref is not there (`kind: "port"`).
 """
 import argparse
 import json
@@ -145,16 +151,51 @@ def cpu_oracle_time(args, n_slices=1, repeats=1):
     return times, torch.get_num_threads()
 
 
+class _stdout_to_stderr:
+    """The reference prints from Python and from its JIT build's subprocesses; keep fd 1 clean for the ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def cpu_reference_time(args, n_slices=1, repeats=1, warmup=0, budget_s=None):
+    """CPU baseline: the unmodified reference from baseline/_ref if installed (kind 'reference'), else the oracle
+    port (kind 'port').  All host threads (torchrun exports OMP_NUM_THREADS=1: set the count explicitly)."""
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    try:
+        from baseline import ref_harness as R
+        if R.available():
+            with _stdout_to_stderr():
+                times, threads = R.time_cpu(args.nf, args.size, n_slices, steps=repeats, warmup=warmup, threads=threads,
+                                            budget_s=budget_s)
+            return times, threads, 'reference'
+    except Exception as e:                                   # noqa: BLE001
+        sys.stderr.write(f"bench: baseline/_ref not usable ({e}); timing the oracle port instead\n")
+    for _ in range(warmup):
+        cpu_oracle_time(args, n_slices)
+    times, threads = cpu_oracle_time(args, n_slices, repeats=repeats)
+    return times, threads, 'port'
+
+
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation of the path on this box's host cores."""
+    """Reference arm: the reference's CPU implementation of the path on this box's host cores (rank 0 only)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    import torch
     n_slices = 1
-    for _ in range(args.warmup):
-        cpu_oracle_time(args, n_slices)
-    times, threads = cpu_oracle_time(args, n_slices, repeats=args.steps)
+    warmup = min(args.warmup, 1)                  # ~4-15 s per slice on the box's cores: one warm-up pass is plenty
+    times, threads, kind = cpu_reference_time(args, n_slices, repeats=args.steps, warmup=warmup, budget_s=240.0)
+    args.steps, args.warmup = len(times), warmup  # steps actually timed (the run is bounded to ~4 minutes)
+    steps = args.steps
     total = sum(times)
     v = n_slices * args.steps / total
     line = {
@@ -162,8 +203,12 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": v, "unit": "slices/s", "cores": threads, "kind": "port",
-                         "sample": f"{n_slices} slice/step of the workload (4-step loop, {args.size}^2, nf={args.nf}), CPU fp32"},
+        "cpu_baseline": {"value": v, "unit": "slices/s", "cores": threads, "kind": kind,
+                         "sample": f"{n_slices} slice per step at B=1 (the reference's own call pattern, engine/test.py:294) of the "
+                                   f"workload: full 4-step loop, {args.size}^2, nf={args.nf}, CPU fp32, upfirdn2d_native; "
+                                   f"{steps} timed steps after {warmup} warm-up"},
+        "note": "CPU arm: fp32 on host cores, bounded sample of the arm's config (the config's batch / precision describe "
+                "the GPU arm's workload)",
         "e2e": {"value": v, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -176,6 +221,76 @@ def workload_config(args):
             "global_batch": args.batch * args.gpus, "per_gpu_batch": args.batch, "size": args.size,
             "precision": args.precision, "parallelism": f"dp{args.gpus} (independent slices, no data-path collective)",
             "l2": "activations per step >> 126 MB L2 (inputs larger than L2)"}
+
+
+def volume_record(args, M, cfg, co, g1, g2, dev, world, rank):
+    """BASELINE configs[2]: `--volumes` synthetic volumes x 155 axial slices x 256^2 through
+    volume.predict_volumes_sharded - contiguous slice shards per rank, one CUDA graph per rank at the balanced shard
+    batch, per-slice RNG streams, pinned host conditioning slices (H2D inside the timed region), ONE all-gather per
+    volume.  Time = max over ranks of the wall clock between two barriers + synchronizes."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from mudiff_b200 import volume as V
+    n_slices, S = 155, args.size
+    per_rank = (n_slices + world - 1) // world
+    gbatch = V.balanced_batch(per_rank, args.batch)
+    sampler = V.GraphSliceSampler(co, g1, g2, cfg.num_timesteps, gbatch, S, cfg.nz, n_cond=3, device=dev)
+    gen = torch.Generator().manual_seed(4242)
+    conds = [(torch.randn(n_slices, 1, S, S, generator=gen).clamp(-3, 3) / 3).pin_memory() for _ in range(3)]
+
+    def run(nv):
+        return V.predict_volumes_sharded(sampler, [conds] * nv, seed=7, first_volume=0, nz=cfg.nz, n_time=cfg.num_timesteps,
+                                         batch=gbatch, device=dev)
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    run(1)                                        # warm-up: NCCL channel set-up, allocator, graph replay
+    sync()
+    t0 = time.perf_counter()
+    full = run(args.volumes)[-1]
+    sync()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = dt.item()
+    total = args.volumes * n_slices
+    return {"workload": f"{args.volumes} volumes x {n_slices} axial slices x {S}^2, slices sharded over {world} rank(s)",
+            "value": total / dt, "unit": "slices/s", "seconds": dt, "shard_slices_per_rank": per_rank,
+            "graph_batch": gbatch, "collective": "one all_gather_into_tensor per volume" if world > 1 else "none (1 rank)",
+            "h2d_bytes": 3 * total * S * S * 4,
+            "checksum_last_volume": hashlib.sha256(full.cpu().numpy().tobytes()).hexdigest()[:16],
+            "note": "checksum is identical for every world size (per-slice RNG streams + batch-invariant kernels)"}
+
+
+def reference_gpu_record(args, value, e2e_value):
+    """The unmodified reference on this GPU (baseline/_ref): engine/test.py's loop, eager, fp16 autocast (:191) with its
+    own upfirdn2d CUDA extension, B=1 (its real call pattern, :294) and B=batch; bounded to a few iterations."""
+    try:
+        from baseline import ref_harness as R
+        if not R.available():
+            return {"unavailable": "baseline/_ref not installed"}
+        import torch
+        with _stdout_to_stderr():
+            models = R.build_models(R.reference_config(args.nf, args.size), torch.device('cuda', torch.cuda.current_device()))
+            rows = [R.time_gpu(args.nf, args.size, 1, 'fp16', iters=5, warmup=3, models=models),
+                    R.time_gpu(args.nf, args.size, args.batch, 'fp16', iters=2, warmup=1, models=models)]
+        out = {"what": "unmodified reference modules + engine/test.py sample_from_model + its upfirdn2d CUDA extension, eager, "
+                       "torch.autocast(float16), same GPU, CUDA events, median",
+               "b1_slices_per_s": rows[0]["slices_per_s"], "b1_ms": rows[0]["ms_median"],
+               f"b{args.batch}_slices_per_s": rows[1]["slices_per_s"], f"b{args.batch}_ms": rows[1]["ms_median"],
+               "cuda_extension_loaded": rows[0]["cuda_extension"],
+               "ours_over_reference_same_batch": value / rows[1]["slices_per_s"],
+               "ours_over_reference_b1": value / rows[0]["slices_per_s"]}
+        if e2e_value:
+            out["ours_e2e_over_reference_same_batch"] = e2e_value / rows[1]["slices_per_s"]
+        return out
+    except Exception as e:                                    # noqa: BLE001
+        return {"unavailable": str(e).splitlines()[0][:200]}
 
 
 def main():
@@ -191,6 +306,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-volume', action='store_true', help='skip the sharded volume-prediction record (configs[2])')
+    ap.add_argument('--no-reference-gpu', action='store_true', help='skip timing the unmodified reference on this GPU')
+    ap.add_argument('--volumes', type=int, default=8)
     ap.add_argument('--breakdown', default='', help="write a per-kernel event-time breakdown to this file ('-' = stderr only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != 'reference':
@@ -373,13 +491,30 @@ def main():
     if key in TFLOP_PER_SLICE:
         e2e_frac = (value / world) * TFLOP_PER_SLICE[key] / pk['tf_sustained']
 
+    launches_per_replay = gs.launches_per_replay
+    # ------------------------------------------------ sharded volume prediction (configs[2]) --
+    vol = None
+    if not args.no_volume and S == 256 and args.nf == 64 and args.precision == 'bf16':
+        try:
+            vol = volume_record(args, M, cfg, co, g1, g2, dev, world, rank)
+        except Exception as e:                                # noqa: BLE001
+            vol = {"error": str(e).splitlines()[0][:200]}
+
+    # ------------------------------------------------ reference on this GPU (rank 0, N == 1) --
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_reference_gpu:
+        del gs, e2e_step, draw_noise              # free the graph's pool before the reference allocates eagerly
+        torch.cuda.empty_cache()
+        ref_gpu = reference_gpu_record(args, value, e2e_value)
+
     # ------------------------------------------------ CPU baseline (rank 0, N == 1) -
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times, threads = cpu_oracle_time(args, 1, repeats=1)
-        cpu = {"value": 1.0 / times[0], "unit": "slices/s", "cores": threads, "kind": "port",
-               "sample": f"1 slice of the workload (full 4-step loop, {S}^2, nf={args.nf}, fp32) through the oracle "
-                         f"port of the reference CPU path; {times[0]:.1f} s"}
+        times, threads, kind = cpu_reference_time(args, 1, repeats=1)
+        cpu = {"value": 1.0 / times[0], "unit": "slices/s", "cores": threads, "kind": kind,
+               "sample": f"1 slice of the workload (full 4-step loop, {S}^2, nf={args.nf}, fp32, B=1) through "
+                         + ("the unmodified reference on CPU tensors (upfirdn2d_native)" if kind == 'reference' else
+                            "the oracle port of the reference CPU path") + f"; {times[0]:.1f} s"}
 
     if rank == 0:
         line = {
@@ -388,9 +523,9 @@ def main():
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args),
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": gs.launches_per_replay * args.steps,
-            "launches_per_step": gs.launches_per_replay,
-            "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches_per_replay * args.steps,
+            "launches_per_step": launches_per_replay,
+            "roofline": roof, "cpu_baseline": cpu, "volume": vol, "reference_gpu": ref_gpu,
             "tensor_roofline_frac_end_to_end": e2e_frac,
         }
         print(json.dumps(line), flush=True)

@@ -234,6 +234,9 @@ int mudiff_scale_to_u8(const float* x, int64_t n, const unsigned int* keys, unsi
 /* Debug: out[0..7] = (timed_out, block, warp, lane, barrier smem address, parity, grid, 0) of the last mbarrier
  * wait that hit its 4e9-cycle bound inside mudiff_conv_tc (kept in mapped host memory). */
 int mudiff_debug_last_timeout(int32_t* out);
+/* Bound (clock64 cycles) of the mbarrier waits inside the tcgen05 kernels; 0 = unbounded (profilers, time-sliced GPUs).
+ * Applies to the current device; synchronising (cudaMemcpyToSymbol). */
+int mudiff_set_wait_timeout(long long cycles);
 int mudiff_debug_dump(int32_t* out, int n);   /* header + the stuck CTA's barrier block / per-warp progress records */
 int mudiff_debug_selftest(void);   /* 1 if the mapped-host debug channel works */
 /* CUDA-core implicit GEMM (fp32 or bf16 storage, fp32 math): any shape, stride 1/2.

@@ -68,6 +68,7 @@ PROTOTYPES = {
     'mudiff_scale_to_u8': [_P, _L, _P, _P, _P],
     'mudiff_debug_last_timeout': [C.POINTER(C.c_int32)],
     'mudiff_debug_dump': [C.POINTER(C.c_int32), _I],
+    'mudiff_set_wait_timeout': [C.c_longlong],
     'mudiff_debug_selftest': [],
     'mudiff_conv_simt': [C.POINTER(ConvDesc), _I, _P],
     'mudiff_stem_conv_tc': [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -105,7 +106,13 @@ class _Proxy:
             if hasattr(cdll, name):
                 setattr(self, name, self._wrap(name, getattr(cdll, name)))
             else:                                   # only possible with MUDIFF_LIB (older debug builds)
-                setattr(self, name, lambda *a: 0)
+                setattr(self, name, self._missing(name))
+
+    @staticmethod
+    def _missing(name):
+        def call(*args):
+            raise RuntimeError(f"mu-diff_b200: the library selected with MUDIFF_LIB does not export {name}")
+        return call
 
     @staticmethod
     def _wrap(name, fn):
@@ -150,7 +157,15 @@ def lib():
         if not alt and l.mudiff_conv_desc_size() != C.sizeof(ConvDesc):
             raise RuntimeError('mu-diff_b200: ConvDesc layout mismatch between _lib.py and the shared library')
         _lib = _Proxy(l)
+        w = os.environ.get('MUDIFF_WAIT_CYCLES')    # bound of the kernels' mbarrier waits; 0 = unbounded (ncu, MPS)
+        if w is not None and torch.cuda.is_available() and hasattr(l, 'mudiff_set_wait_timeout'):
+            set_wait_timeout(int(w))
     return _lib
+
+
+def set_wait_timeout(cycles: int):
+    """Bound (clock64 cycles, 0 = none) of the mbarrier waits in the tcgen05 kernels on the CURRENT device."""
+    check(lib().mudiff_set_wait_timeout(int(cycles)), 'set_wait_timeout')
 
 
 def dtype_code(t: torch.dtype) -> int:

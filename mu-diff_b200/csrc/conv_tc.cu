@@ -93,6 +93,10 @@ __device__ int* g_dbg_host = nullptr;         // device pointer of a pinned, map
 __device__ int g_dbg_lock = 0;                // first timed-out waiter writes the record
 constexpr int kDbgRecOff = 640;               // byte offset of the per-warp records inside the barrier block
 __device__ int g_dbg_done = 0;
+// Bound of every mbarrier wait in clock64 cycles (default 4e9 ~ 2 s); 0 = wait forever.  Settable through
+// mudiff_set_wait_timeout() / the MUDIFF_WAIT_CYCLES environment variable: a time-sliced or preempted GPU, or a long
+// profiler replay, can legitimately stall a CTA for longer than any fixed bound.
+__device__ long long g_wait_cycles = 4000000000LL;
 __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity, const uint8_t* bar_block) {
   int* d = g_dbg_host;
   if (d) {
@@ -121,7 +125,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const 
   }
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity, bar_block);
+    const long long lim = *(volatile long long*)&g_wait_cycles;
+    if (lim > 0 && clock64() - t0 > lim) mbar_timeout(bar, parity, bar_block);
   }
   if ((threadIdx.x & 31) == 0) rec[3] = 0;
 }
@@ -882,6 +887,11 @@ extern "C" int mudiff_debug_selftest(void) {
   dbg_selftest_kernel<<<1, 1>>>();
   if (cudaDeviceSynchronize() != cudaSuccess) return -2;
   return ((volatile int*)g_dbg_host_ptr)[8] == 12345 ? 1 : 0;
+}
+
+extern "C" int mudiff_set_wait_timeout(long long cycles) {
+  if (cycles < 0) return MUDIFF_EINVAL;
+  return (int)cudaMemcpyToSymbol(g_wait_cycles, &cycles, sizeof(cycles));
 }
 
 extern "C" int mudiff_debug_last_timeout(int32_t* out) {

@@ -1,5 +1,10 @@
-"""`dense()` factory with the reference's initialisation (backbones/dense_layer.py:63-71):
-nn.Linear with fan-avg uniform weights (gain `init_scale`, 0 -> 1e-10) and zero bias."""
+"""`dense()` factory with the reference's initialisation (backbones/dense_layer.py:63-71): nn.Linear with uniform
+weights (gain `init_scale`, 0 -> 1e-10) and zero bias.
+
+The reference asks for mode='fan_avg' but its `_calculate_correct_fan` (dense_layer.py:22-32) returns
+`fan_in if mode == 'fan_in' else fan_out`, i.e. 'fan_avg' silently means fan_OUT: bound = sqrt(3 * gain / fan_out).
+That quirk is reproduced here so that randomly initialised modules have the reference's weight scale (it does not
+matter for loaded checkpoints)."""
 import math
 
 import torch
@@ -8,12 +13,11 @@ from torch import nn
 
 def variance_scaling_init_(tensor, scale):
     gain = 1e-10 if scale == 0 else scale
-    fan_out, fan_in = tensor.shape[0], tensor.shape[1]
     rf = 1
     for d in tensor.shape[2:]:
         rf *= d
-    fan_avg = (fan_in * rf + fan_out * rf) / 2.0
-    bound = math.sqrt(3.0 * gain / max(1.0, fan_avg))
+    fan_out = tensor.shape[0] * rf                # torch.nn.init._calculate_fan_in_and_fan_out: size(0) * receptive field
+    bound = math.sqrt(3.0 * gain / max(1.0, fan_out))
     with torch.no_grad():
         return tensor.uniform_(-bound, bound)
 

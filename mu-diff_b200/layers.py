@@ -36,8 +36,13 @@ def default_init(scale=1.):
 
 
 class PackCache:
-    """Caches kernel-ready (packed / cast) copies of parameters; invalidated when a
-    parameter is modified in place (load_state_dict bumps `_version`) or replaced."""
+    """Caches kernel-ready (packed / cast) copies of parameters; rebuilt when a parameter is modified in place
+    (optimizer step, load_state_dict: `_version` bumps) or replaced.
+
+    A rebuilt copy is written INTO the tensor of the previous copy whenever shape and dtype still match, so its device
+    address never changes: a captured CUDA graph that embeds the address stays valid across weight updates and only
+    needs `refresh_packs(module)` (validation.ValidationSampler).  For that to be safe a cached value never aliases a
+    parameter (an fp32 `.float().contiguous()` of an fp32 parameter would): such values are cloned."""
 
     def _packed(self, key, params, builder):
         cache = self.__dict__.setdefault('_pack_cache', {})
@@ -46,9 +51,49 @@ class PackCache:
         if hit is not None and hit[0] == sig:
             return hit[1]
         with torch.no_grad():
-            val = builder()
-        cache[key] = (sig, val)
+            val = _own(builder(), params)
+            if hit is not None and _same_layout(hit[1], val):
+                _copy_into(hit[1], val)
+                val = hit[1]
+        cache[key] = (sig, val, list(params), builder)
         return val
+
+
+def _own(val, params):
+    if isinstance(val, (tuple, list)):
+        return type(val)(_own(v, params) for v in val)
+    if torch.is_tensor(val) and any(val.untyped_storage().data_ptr() == p.untyped_storage().data_ptr() for p in params):
+        return val.clone()
+    return val
+
+
+def _same_layout(a, b):
+    if isinstance(a, (tuple, list)):
+        return isinstance(b, (tuple, list)) and len(a) == len(b) and all(_same_layout(x, y) for x, y in zip(a, b))
+    return (torch.is_tensor(a) and torch.is_tensor(b) and a.shape == b.shape and a.dtype == b.dtype
+            and a.device == b.device and a.stride() == b.stride())
+
+
+def _copy_into(dst, src):
+    if isinstance(dst, (tuple, list)):
+        for d, s_ in zip(dst, src):
+            _copy_into(d, s_)
+    else:
+        dst.copy_(src)
+
+
+def refresh_packs(root: nn.Module) -> int:
+    """Re-evaluate every cached packed copy under `root` whose parameters changed, in place (addresses kept).
+    Returns the number of cache entries visited."""
+    n = 0
+    for m in root.modules():
+        cache = m.__dict__.get('_pack_cache')
+        if not cache:
+            continue
+        for key, entry in list(cache.items()):
+            m._packed(key, entry[2], entry[3])
+            n += 1
+    return n
 
 
 class Conv2d(nn.Module, PackCache):

@@ -301,7 +301,7 @@ class ResnetBlockBigGANpp_Adagn(nn.Module, layers.PackCache):
             # Conv_1(h) + Conv_2(x) as ONE contraction: K = 9*Cout + Cin   (layerspp.py:316-324)
             c2 = self.Conv_2
             wt = self._packed(('w12', dt, tuple(seg_c)), [self.Conv_1.weight, c2.weight],
-                              lambda: torch.cat([w1, c2.packed_weight(dt, seg_c)], dim=1).contiguous())
+                              lambda: torch.cat([self.Conv_1.packed_weight(dt), c2.packed_weight(dt, seg_c)], dim=1).contiguous())
             bias = self._packed(('b12',), [self.Conv_1.bias, c2.bias],
                                 lambda: (self.Conv_1.bias + c2.bias).detach().float().contiguous())
             return ops.conv([hseg] + [(t, 1) for t in xs], wt, self.out_ch, bias=bias, alpha=sc, want_stats=True)

@@ -84,6 +84,11 @@ def sample_posterior_combine(coefficients, x_0_1, x_0_2, x_t, t, noise=None):
                                 coefficients.posterior_mean_coef2, coefficients.posterior_log_variance_clipped)
 
 
+def _ch0(x):
+    """`x[:, [0], :]` of engine/test.py:193-195 as a view (no gather kernel; identical values)."""
+    return x[:, 0:1]
+
+
 def sample_from_model(coefficients, generator1, cond1, generator2, cond2, cond3, n_time, x_init, T, opt,
                       latents=None, noises=None):
     """engine/test.py:180-199.  `T` is accepted and unused, as in the reference.  For the
@@ -97,8 +102,8 @@ def sample_from_model(coefficients, generator1, cond1, generator2, cond2, cond3,
             t = torch.full((x.size(0),), i, dtype=torch.int64, device=x.device)
             latent_z = latents[i] if latents is not None else torch.randn(x.size(0), opt.nz, device=x.device)
             x_0_1 = generator1(x, *conds, t, latent_z)
-            x_0_2 = generator2(x, *conds, t, latent_z, x_0_1[:, [0], :])
-            x_new = sample_posterior_combine(coefficients, x_0_1[:, [0], :], x_0_2[:, [0], :], x, t,
+            x_0_2 = generator2(x, *conds, t, latent_z, _ch0(x_0_1))
+            x_new = sample_posterior_combine(coefficients, _ch0(x_0_1), _ch0(x_0_2), x, t,
                                              noise=noises[i] if noises is not None else None)
             x = x_new.detach()
     return x
@@ -138,8 +143,8 @@ class GraphSampler:
         with torch.no_grad():
             for i in reversed(range(self.n_time)):
                 x01 = self.g1(x, *self.conds, self.ts[i], self.latents[i])
-                x02 = self.g2(x, *self.conds, self.ts[i], self.latents[i], x01)
-                x = sample_posterior_combine(self.co, x01, x02, x, self.ts[i], noise=self.noises[i])
+                x02 = self.g2(x, *self.conds, self.ts[i], self.latents[i], _ch0(x01))      # engine/test.py:193
+                x = sample_posterior_combine(self.co, _ch0(x01), _ch0(x02), x, self.ts[i], noise=self.noises[i])
         return x
 
     def load(self, conds, x_init, latents, noises, non_blocking=True):
@@ -152,9 +157,12 @@ class GraphSampler:
             d.copy_(s, non_blocking=non_blocking)
 
     def replay(self):
+        """Replay the graph; returns the graph's STATIC output buffer (overwritten by the next replay - copy it if it
+        has to outlive that, as `run` does)."""
         self.graph.replay()
         return self.out
 
     def run(self, conds, x_init, latents, noises):
+        """Copy new inputs in, replay, return a fresh tensor owned by the caller (like the reference's loop)."""
         self.load(conds, x_init, latents, noises)
-        return self.replay()
+        return self.replay().clone()

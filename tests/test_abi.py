@@ -138,3 +138,26 @@ def test_validation_share_weights_aliases_training_parameters():
     k0 = next(iter(tp))
     assert torch.equal(tp[k0], fp[k0])
     assert VAL.params_signature((fast_g,)) != sig0
+
+
+def test_pack_cache_refreshes_in_place():
+    """layers.PackCache: a packed copy never aliases its parameter, and after an in-place weight update (or a
+    load_state_dict) the copy is rebuilt INTO the same tensor, so a captured CUDA graph that embeds its address stays
+    valid (validation.ValidationSampler relies on this)."""
+    import torch
+    import mudiff_b200 as M
+    conv = M.layers.ddpm_conv3x3(8, 16)
+    w0 = conv.packed_weight(torch.bfloat16)
+    b0 = conv.bias_f32()
+    assert b0.data_ptr() != conv.bias.data_ptr()                   # fp32 -> fp32 "cast" must still be a copy
+    ptr_w, ptr_b, snap = w0.data_ptr(), b0.data_ptr(), w0.clone()
+    with torch.no_grad():
+        conv.weight.mul_(2.0)
+        conv.bias.add_(1.0)
+    assert M.layers.refresh_packs(conv) == 2
+    w1, b1 = conv.packed_weight(torch.bfloat16), conv.bias_f32()
+    assert w1.data_ptr() == ptr_w and b1.data_ptr() == ptr_b
+    assert torch.equal(w1.float(), snap.float() * 2.0) and torch.equal(b1, conv.bias.detach())
+    conv.load_state_dict({'weight': torch.ones_like(conv.weight), 'bias': torch.zeros_like(conv.bias)})
+    assert conv.packed_weight(torch.bfloat16).data_ptr() == ptr_w
+    assert float(conv.packed_weight(torch.bfloat16).float().min()) == 1.0

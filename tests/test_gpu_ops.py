@@ -632,3 +632,32 @@ def test_testset_driver_kernels_vs_oracle(M, tmp_path):
     from PIL import Image
     back = np.array(Image.open(tmp_path / 'out' / 'pred' / 'pred_00003.png'))
     np.testing.assert_array_equal(back, p8[3])
+
+
+def test_testset_driver_vs_reference_fixture(M, golden_dir, tmp_path):
+    """SURVEY 8f row 2 against the REFERENCE: tests/golden/testset.npz holds what the reference's
+    BratsDataset.__getitem__ (dataset/dataset_brats.py:73-92) returned for a `.npy` split and what the export block of
+    engine/test.py:367-388 wrote; the split is re-created on disk here and goes through load_split -> zscore_to_unit
+    (device) and export_uint8 (device), bit for bit, for all four target modalities."""
+    from mudiff_b200 import testset as T
+    g = np.load(os.path.join(golden_dir, 'testset.npz'))
+    split = tmp_path / 'test'
+    split.mkdir()
+    for m in ('FLAIR', 'T2', 'T1', 'T1CE'):
+        np.save(split / f'{m}.npy', g[f'in_{m}'])
+    for target in ('T1CE', 'FLAIR', 'T2', 'T1'):
+        arrays = T.load_split(str(tmp_path), 'test', target)
+        assert T.ORDERS[target] == list(g[f'{target}_order'])
+        for j in range(3):
+            got = T.zscore_to_unit(torch.from_numpy(arrays[j]).cuda()).cpu().numpy()
+            np.testing.assert_array_equal(got, g[f'{target}_cond'][:, j])
+        got = T.zscore_to_unit(torch.from_numpy(arrays[3]).cuda()).cpu().numpy()
+        np.testing.assert_array_equal(got, g[f'{target}_target'][:, 0])
+    for tag in ('a', 'b', 'const'):
+        pred = torch.from_numpy(g[f'exp_{tag}_pred']).unsqueeze(1).cuda()
+        gt = torch.from_numpy(g[f'exp_{tag}_gt']).unsqueeze(1).cuda()
+        p8, g8, (lo, hi) = T.export_uint8(pred, gt)
+        np.testing.assert_array_equal(p8, g[f'exp_{tag}_p8'])
+        np.testing.assert_array_equal(g8, g[f'exp_{tag}_g8'])
+        if tag != 'const':
+            assert (np.float32(lo), np.float32(hi)) == tuple(np.float32(v) for v in g[f'exp_{tag}_win'])

@@ -119,3 +119,20 @@ def test_volume_oracle_matches_reference_golden(golden_dir, name):
     np.testing.assert_array_equal(conds.numpy(), g[f'{name}_conds'])
     pred = VO.postprocess_slices(torch.from_numpy(g[f'{name}_fake']))
     np.testing.assert_array_equal(VO.reconstruct_volume_from_slices(list(pred), vol.shape, s0, s1), g[f'{name}_rebuilt'])
+
+
+def test_testset_oracle_vs_reference_fixture(golden_dir):
+    """oracle/testset_oracle.py against tests/golden/testset.npz, which make_testset_golden.py produced by running the
+    reference's BratsDataset.__getitem__ (dataset/dataset_brats.py:73-92) and the export block of engine/test.py:367-388."""
+    from oracle import testset_oracle as TO
+    g = _npz(golden_dir, 'testset.npz')
+    for target in ('T1CE', 'FLAIR', 'T2', 'T1'):
+        order = list(g[f'{target}_order'])
+        for j, m in enumerate(order[:-1]):
+            np.testing.assert_array_equal(TO.zscore_to_unit(g[f'in_{m}']).numpy(), g[f'{target}_cond'][:, j])
+        np.testing.assert_array_equal(TO.zscore_to_unit(g[f'in_{order[-1]}']).numpy(), g[f'{target}_target'][:, 0])
+    for tag in ('a', 'b', 'const'):
+        p8, g8, (lo, hi) = TO.export_uint8(list(g[f'exp_{tag}_pred']), list(g[f'exp_{tag}_gt']))
+        np.testing.assert_array_equal(p8, g[f'exp_{tag}_p8'])
+        np.testing.assert_array_equal(g8, g[f'exp_{tag}_g8'])
+        assert (lo, hi) == tuple(g[f'exp_{tag}_win'])
