@@ -172,7 +172,7 @@ def time_gpu(nf=64, size=256, batch=1, mode='fp16', iters=10, warmup=3, device='
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
     med = statistics.median(times)
-    import utils.op.upfirdn2d as U
+    U = sys.modules['utils.op.upfirdn2d']         # (`utils.op.upfirdn2d` the attribute is the function, not the module)
     return {"mode": mode, "batch": batch, "size": size, "nf": nf, "iters": iters, "warmup": warmup,
             "ms_best": min(times), "ms_median": med, "slices_per_s": batch / (med * 1e-3),
             "slices_per_s_best": batch / (min(times) * 1e-3), "finite": ok,

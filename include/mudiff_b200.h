@@ -36,6 +36,7 @@ extern "C" {
 #define MUDIFF_ACT_SILU 1
 #define MUDIFF_ACT_SIGMOID 2
 #define MUDIFF_ACT_TANH 3
+#define MUDIFF_ACT_LRELU 4   /* LeakyReLU(0.2): the discriminator's activation (backbones/discriminator.py:178) */
 
 /* ABI version + build info (static string). */
 int mudiff_abi_version(void);
@@ -68,6 +69,14 @@ int mudiff_upfirdn2d(const void* in, void* out, const float* kernel, int dtype,
 int mudiff_fused_bias_act(const void* x, const void* bias, const void* ref, void* out, int dtype,
                           int64_t n, int size_b, int64_t step_b, int act, int grad,
                           float alpha, float scale, void* stream);
+
+/* Minibatch standard deviation feature of Discriminator_large.forward (backbones/discriminator.py:243-250):
+ * x = channels-last [batch, hw, C] (pixel stride ld), group = min(batch, 4), n_sub = batch / group;
+ * s[m] = mean over (c, pixel) of sqrt(var over g of x[g * n_sub + m] + 1e-8) (biased variance);
+ * writes s[b % n_sub] into channel `out_c` of out (channels-last, pixel stride out_ld) for every pixel of sample b.
+ * dtype = dtype of x and out.  batch must be a multiple of group. */
+int mudiff_minibatch_stddev(const void* x, int ld, void* out, int out_ld, int out_c, int dtype,
+                            int batch, int group, int channels, int hw, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Posterior update, one fused kernel.  Replaces sample_posterior_combine

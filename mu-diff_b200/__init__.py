@@ -11,12 +11,14 @@ package at the repository root.  Layout mirrors the reference for the path only:
     volume.py                engine/test_volume.py:135-181,269-294 (sharded, batched, GPU pre/post)
     testset.py               engine/test.py:265-400 (batched slice-test driver, uint8 export)
     validation.py            engine/train.py:1148-1175 (validation sampling on weights shared with training)
+    discriminator.py         backbones/discriminator.py (Discriminator_large forward)
     csrc/, libmudiff_b200.so C ABI (include/mudiff_b200.h)
 """
 from . import _lib, ops  # noqa: F401
 from . import op  # noqa: F401
 from . import layers, dense_layer, up_or_down_sampling, layerspp  # noqa: F401
 from . import ncsnpp_generator_adagn_feat, ncsnpp_generator_adagn_feat_healthy  # noqa: F401
+from . import discriminator  # noqa: F401
 from .ncsnpp_generator_adagn_feat import NCSNpp, NCSNpp_adaptive  # noqa: F401
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d, upfirdn2d_ada  # noqa: F401
 from .sampling import (GraphSampler, Posterior_Coefficients, get_sigma_schedule, get_time_schedule,  # noqa: F401

@@ -11,7 +11,7 @@ import os
 import torch
 
 F32, BF16, F16 = 0, 1, 2
-ACT_NONE, ACT_SILU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_SIGMOID, ACT_TANH, ACT_LRELU = 0, 1, 2, 3, 4
 EINVAL, EUNSUPPORTED = -22, -95
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -66,6 +66,7 @@ PROTOTYPES = {
     'mudiff_minmax_keys': [_P, _L, _I, _P, _P],
     'mudiff_minmax_read': [_P, _P, _P],
     'mudiff_scale_to_u8': [_P, _L, _P, _P, _P],
+    'mudiff_minibatch_stddev': [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'mudiff_debug_last_timeout': [C.POINTER(C.c_int32)],
     'mudiff_debug_dump': [C.POINTER(C.c_int32), _I],
     'mudiff_set_wait_timeout': [C.c_longlong],

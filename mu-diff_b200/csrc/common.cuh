@@ -94,6 +94,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case MUDIFF_ACT_SILU: return silu_exact(v);
     case MUDIFF_ACT_SIGMOID: return sigmoid_exact(v);
     case MUDIFF_ACT_TANH: return tanhf(v);
+    case MUDIFF_ACT_LRELU: return v > 0.f ? v : 0.2f * v;
     default: return v;
   }
 }

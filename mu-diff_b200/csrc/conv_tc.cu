@@ -510,6 +510,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             } else if (p.act == MUDIFF_ACT_TANH) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+            } else if (p.act == MUDIFF_ACT_LRELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
             }
             if (kOutF32) {
               float4* op = reinterpret_cast<float4*>((float*)p.out + pix * p.out_ld + p.out_coff + n);

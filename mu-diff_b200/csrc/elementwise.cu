@@ -376,6 +376,56 @@ extern "C" int mudiff_fused_bias_act(const void* x, const void* bias, const void
   DISPATCH3(dtype, launch_bias_act, x, bias, ref, out, n, size_b, step_b, act, grad, alpha, scale, st);
 }
 
+// minibatch standard deviation (backbones/discriminator.py:243-250): one block per sub-batch index m
+template <typename T>
+__global__ void __launch_bounds__(256) mbstd_kernel(const T* __restrict__ x, int ld, T* __restrict__ out, int out_ld, int out_c,
+                                                    int n_sub, int group, int channels, int hw) {
+  const int m = blockIdx.x;
+  const int64_t per = (int64_t)channels * hw;
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < per; i += blockDim.x) {
+    const int64_t pix = i / channels;
+    const int c = (int)(i - pix * channels);
+    float v[8], mean = 0.f;
+    for (int g = 0; g < group; ++g) {
+      v[g] = Cvt<T>::to_f(x[((int64_t)(g * n_sub + m) * hw + pix) * ld + c]);
+      mean += v[g];
+    }
+    mean /= (float)group;
+    float var = 0.f;
+    for (int g = 0; g < group; ++g) var += (v[g] - mean) * (v[g] - mean);
+    acc += sqrtf(var / (float)group + 1e-8f);
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {                       // fixed-order tree: deterministic
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  const T sv = Cvt<T>::from_f(red[0] / (float)per);
+  for (int64_t i = threadIdx.x; i < (int64_t)group * hw; i += blockDim.x) {
+    const int g = (int)(i / hw);
+    const int64_t pix = i - (int64_t)g * hw;
+    out[((int64_t)(g * n_sub + m) * hw + pix) * out_ld + out_c] = sv;
+  }
+}
+
+template <typename T>
+static int launch_mbstd(const void* x, int ld, void* out, int out_ld, int out_c, int n_sub, int group, int channels, int hw,
+                        cudaStream_t st) {
+  mbstd_kernel<T><<<n_sub, 256, 0, st>>>((const T*)x, ld, (T*)out, out_ld, out_c, n_sub, group, channels, hw);
+  return mudiff_launch_status();
+}
+
+extern "C" int mudiff_minibatch_stddev(const void* x, int ld, void* out, int out_ld, int out_c, int dtype,
+                                       int batch, int group, int channels, int hw, void* stream) {
+  if (!x || !out || batch <= 0 || group <= 0 || group > 8 || channels <= 0 || hw <= 0 || batch % group) return MUDIFF_EINVAL;
+  if (ld < channels || out_c < 0 || out_c >= out_ld) return MUDIFF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH3(dtype, launch_mbstd, x, ld, out, out_ld, out_c, batch / group, group, channels, hw, st);
+}
+
 extern "C" int mudiff_posterior_update(const float* x01, int64_t x01_bstride, const float* x02, int64_t x02_bstride,
                                        const float* xt, const float* noise, const int64_t* t,
                                        const float* coef1, const float* coef2, const float* logvar, int n_steps,

@@ -27,3 +27,16 @@ def dense(in_channels, out_channels, init_scale=1.):
     variance_scaling_init_(lin.weight, scale=init_scale)
     nn.init.zeros_(lin.bias)
     return lin
+
+
+def conv2d(in_planes, out_planes, kernel_size=(3, 3), stride=1, dilation=1, padding=1, bias=True, padding_mode='zeros',
+           init_scale=1.):
+    """backbones/dense_layer.py:73-81 (the discriminator's conv factory): an nn.Conv2d-compatible module (`weight`
+    [Cout, Cin, k, k], `bias`) that runs on the libmudiff_b200 conv kernels, with the reference's initialisation."""
+    from . import layers
+    k = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
+    if stride != 1 or dilation != 1 or padding_mode != 'zeros' or padding != k // 2:
+        raise NotImplementedError("mu-diff_b200 conv2d: stride 1, dilation 1, zero 'same' padding")
+    conv = layers.Conv2d(in_planes, out_planes, k, bias=bias, stride=1, padding=padding)
+    variance_scaling_init_(conv.weight, scale=init_scale)
+    return conv

@@ -567,6 +567,28 @@ def softmax_rows_(x2d, scale=1.0):
     return x2d
 
 
+def leaky_relu(x, slope=0.2):
+    """LeakyReLU(slope) of a dense tensor (any layout; `mudiff_fused_bias_act` without bias, scale 1)."""
+    L.require_cuda(x)
+    if not (x.is_contiguous() or (x.ndim == 4 and is_nhwc_view(x) and _pix_ld(x) == x.shape[1])):
+        x = as_nhwc(x.contiguous())
+    out = torch.empty_like(x)
+    L.check(L.lib().mudiff_fused_bias_act(x.data_ptr(), None, None, out.data_ptr(), L.dtype_code(x.dtype), x.numel(), 1, 1,
+                                          3, 0, float(slope), 1.0, L.stream_ptr(x.device)), 'fused_bias_act')
+    return out
+
+
+def minibatch_stddev(x, out, out_c, group):
+    """Writes the minibatch-stddev feature of x (backbones/discriminator.py:243-250) into channel `out_c` of `out`."""
+    x = as_nhwc(x)
+    b, c, h, w = x.shape
+    xin = x if x.dtype == out.dtype else x.to(out.dtype)
+    L.check(L.lib().mudiff_minibatch_stddev(xin.data_ptr(), _pix_ld(xin), out.data_ptr(), _pix_ld(out), out_c,
+                                            L.dtype_code(out.dtype), b, group, c, h * w, L.stream_ptr(x.device)),
+            'minibatch_stddev')
+    return out
+
+
 def posterior_update(x01, x02, xt, noise, t, coef1, coef2, logvar):
     """engine/test.py:150-177 as one kernel (fp32)."""
     L.require_cuda(x01, x02, xt, noise, t)

@@ -450,3 +450,31 @@ def test_size_128_loop_bf16_and_fp32_vs_oracle(M):
             assert err <= 1e-4
         else:
             _bf16_gate(x, ref, '4-step loop nf64 128^2 B=2')
+
+
+# ---- discriminator forward ---------------------------------------------------------------------------
+@pytest.mark.parametrize('tag,ngf,temb,size,batch', [('ngf16_s128_b8', 16, 128, 128, 8), ('ngf64_s64_b4', 64, 256, 64, 4),
+                                                     ('ngf16_s64_b2', 16, 64, 64, 2)])
+def test_discriminator_vs_reference_golden(M, golden_dir, tag, ngf, temb, size, batch):
+    """Discriminator_large.forward(x, t, x_t) (backbones/discriminator.py:216-263): fp32 path max-abs <= 1e-4 against the
+    reference-generated fixture (logits and mid_feat); bf16 tensor-core path (ngf=64: tcgen05 convs) within the bf16
+    gate on mid_feat and 2e-2 absolute on the logits.  state_dict keys are the reference's (strict load)."""
+    from oracle import disc_oracle as DO
+    from tests.test_oracle import disc_inputs
+    g = np.load(os.path.join(golden_dir, 'disc.npz'))
+    sd = DO.make_state_dict(nc=2, ngf=ngf, t_emb_dim=temb, seed=3)
+    x, x_t, t = disc_inputs(g, tag, size, batch)
+    for prec in ('fp32', 'bf16'):
+        D = M.discriminator.Discriminator_large(nc=2, ngf=ngf, t_emb_dim=temb, act=torch.nn.LeakyReLU(0.2), precision=prec).to(DEV).eval()
+        D.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            logits, mid = D(x.to(DEV), t.to(DEV), x_t.to(DEV))
+        assert tuple(logits.shape) == (batch,) and tuple(mid.shape) == g[f'{tag}_mid'].shape
+        el = np.abs(logits.float().cpu().numpy() - g[f'{tag}_logits']).max()
+        em = np.abs(mid.float().cpu().numpy() - g[f'{tag}_mid']).max()
+        rel = np.linalg.norm(mid.float().cpu().numpy() - g[f'{tag}_mid']) / np.linalg.norm(g[f'{tag}_mid'])
+        print(f"[disc {prec}] {tag}: logits max|err|={el:.3e}  mid max|err|={em:.3e} rel_l2={rel:.3e}")
+        if prec == 'fp32':
+            assert el <= 1e-4 and em <= 1e-4, (el, em)
+        else:
+            assert rel <= 2e-2 and el <= 2e-2, (rel, el)

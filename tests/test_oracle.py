@@ -136,3 +136,24 @@ def test_testset_oracle_vs_reference_fixture(golden_dir):
         np.testing.assert_array_equal(p8, g[f'exp_{tag}_p8'])
         np.testing.assert_array_equal(g8, g[f'exp_{tag}_g8'])
         assert (lo, hi) == tuple(g[f'exp_{tag}_win'])
+
+
+def test_discriminator_oracle_vs_reference_fixture(golden_dir):
+    """oracle/disc_oracle.py against tests/golden/disc.npz (the reference's Discriminator_large run on CPU)."""
+    from oracle import disc_oracle as DO
+    g = _npz(golden_dir, 'disc.npz')
+    for tag, ngf, temb, size, batch in (('ngf16_s128_b8', 16, 128, 128, 8), ('ngf64_s64_b4', 64, 256, 64, 4),
+                                        ('ngf16_s64_b2', 16, 64, 64, 2)):
+        sd = DO.make_state_dict(nc=2, ngf=ngf, t_emb_dim=temb, seed=3)
+        x, x_t, t = disc_inputs(g, tag, size, batch)
+        logits, mid = DO.discriminator_forward(sd, x, t, x_t)
+        np.testing.assert_allclose(logits.numpy(), g[f'{tag}_logits'], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(mid.numpy(), g[f'{tag}_mid'], rtol=0, atol=2e-6)
+
+
+def disc_inputs(g, tag, size, batch):
+    """Re-draw the inputs make_disc_golden.py used (same CPU generator seed), guarded by the stored sums."""
+    gen = torch.Generator().manual_seed(17)
+    x, x_t = torch.randn(batch, 1, size, size, generator=gen), torch.randn(batch, 1, size, size, generator=gen)
+    np.testing.assert_allclose([x.double().sum().item(), x_t.double().sum().item()], g[f'{tag}_xsum'], rtol=0, atol=1e-9)
+    return x, x_t, torch.from_numpy(g[f'{tag}_t'])
