@@ -19,6 +19,8 @@ Prints ONE JSON line (rank 0).  Keys: see the driver contract; additionally
   volume       : BASELINE configs[2] shape through volume.predict_volumes_sharded: 8 volumes x 155 axial slices x 256^2,
                  slices sharded over the N ranks, one CUDA graph per rank at the balanced shard batch, ONE NCCL
                  all-gather per volume (the path's only collective); slices/s = all slices / max-over-ranks time
+  other_configs: (N = 1) short device-resident timings of BASELINE configs[0] (B = 1), [3] (healthy, B = 128), the corners of
+                 [4] (128^2, 512^2), nf = 128 and the fp32 path - so that they are in the driver's record
   reference_gpu: (N = 1) the UNMODIFIED reference (baseline/_ref, its own loop + CUDA extensions, eager, fp16 autocast
                  as engine/test.py:191) timed on the same GPU at B=1 and B=64 - the north star's ">= 25x" denominator
 `--impl reference` times the reference's own CPU implementation of the path on all host threads: the UNMODIFIED
@@ -267,6 +269,65 @@ def volume_record(args, M, cfg, co, g1, g2, dev, world, rank):
             "note": "checksum is identical for every world size (per-slice RNG streams + batch-invariant kernels)"}
 
 
+def other_configs_record(args, dev):
+    """Short device-resident timings (3 warm-up + 3 timed graph replays each, CUDA events) of the other BASELINE.json
+    configurations, so that they are in the driver's record and not only in builder-side sweeps: configs[0] (B = 1, the
+    reference's own call pattern), configs[3] (healthy 2-contrast variant, B = 128), the corners of configs[4] (128^2 and
+    512^2), the production width nf = 128 (experiments/cfg/local.yaml:26) and the fp32 parity path of configs[1]."""
+    import torch
+    import mudiff_b200 as M
+    from mudiff_b200.utils import randomize_
+    plan = [("configs[0]: main, 256^2, B=1", dict(nf=64, size=256, batch=1, prec='bf16', healthy=False)),
+            ("configs[3]: healthy variant, 256^2, B=128", dict(nf=64, size=256, batch=128, prec='bf16', healthy=True)),
+            ("configs[4]: main, 128^2, B=256", dict(nf=64, size=128, batch=256, prec='bf16', healthy=False)),
+            ("configs[4]: main, 512^2, B=16", dict(nf=64, size=512, batch=16, prec='bf16', healthy=False)),
+            ("nf=128 (local.yaml), 256^2, B=16", dict(nf=128, size=256, batch=16, prec='bf16', healthy=False)),
+            ("configs[1] fp32 path, 256^2, B=16", dict(nf=64, size=256, batch=16, prec='fp32', healthy=False))]
+    pk = peaks()
+    out = []
+    for name, c in plan:
+        try:
+            a = Namespace(nf=c['nf'], size=c['size'], precision=c['prec'])
+            cfg = build_cfg(a)
+            mod = M.ncsnpp_generator_adagn_feat_healthy if c['healthy'] else M.ncsnpp_generator_adagn_feat
+            g1 = randomize_(mod.NCSNpp(cfg), 0).to(dev).eval()
+            g2 = randomize_(mod.NCSNpp_adaptive(cfg), 1).to(dev).eval()
+            co = M.Posterior_Coefficients(cfg, dev)
+            gs = M.GraphSampler(co, g1, g2, cfg.num_timesteps, c['batch'], c['size'], cfg.nz,
+                                n_cond=2 if c['healthy'] else 3, device=dev, warmup=1)
+            gen = torch.Generator(device=dev).manual_seed(99)
+            for t in gs.conds:
+                t.normal_(generator=gen).clamp_(-3, 3).div_(3)
+            gs.x_init.normal_(generator=gen)
+            for t in gs.latents + gs.noises:
+                t.normal_(generator=gen)
+            for _ in range(3):
+                gs.replay()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 3
+            e0.record()
+            for _ in range(n):
+                y = gs.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / n
+            rec = {"config": name, "precision": c['prec'], "slices_per_s": c['batch'] / (ms * 1e-3), "ms_per_step": ms,
+                   "launches_per_step": gs.launches_per_replay, "finite": bool(torch.isfinite(y).all().item())}
+            key = (c['nf'], c['size'])
+            if not c['healthy'] and c['prec'] == 'bf16' and key in TFLOP_PER_SLICE:
+                rec["tensor_roofline_frac"] = rec["slices_per_s"] * TFLOP_PER_SLICE[key] / pk['tf_sustained']
+            if c['healthy'] and c['prec'] == 'bf16':
+                rec["tensor_roofline_frac"] = rec["slices_per_s"] * 2.972 / pk['tf_sustained']     # SURVEY 8d: healthy nf=64 256^2
+            out.append(rec)
+            del gs, g1, g2
+            torch.cuda.empty_cache()
+        except Exception as e:                                # noqa: BLE001
+            out.append({"config": name, "error": str(e).splitlines()[0][:200]})
+            torch.cuda.empty_cache()
+    return out
+
+
 def reference_gpu_record(args, value, e2e_value):
     """The unmodified reference on this GPU (baseline/_ref): engine/test.py's loop, eager, fp16 autocast (:191) with its
     own upfirdn2d CUDA extension, B=1 (its real call pattern, :294) and B=batch; bounded to a few iterations."""
@@ -308,6 +369,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-volume', action='store_true', help='skip the sharded volume-prediction record (configs[2])')
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip timing the unmodified reference on this GPU')
+    ap.add_argument('--no-other-configs', action='store_true', help='skip the short timings of the other BASELINE configs')
     ap.add_argument('--volumes', type=int, default=8)
     ap.add_argument('--breakdown', default='', help="write a per-kernel event-time breakdown to this file ('-' = stderr only)")
     args = ap.parse_args()
@@ -500,12 +562,15 @@ def main():
         except Exception as e:                                # noqa: BLE001
             vol = {"error": str(e).splitlines()[0][:200]}
 
-    # ------------------------------------------------ reference on this GPU (rank 0, N == 1) --
-    ref_gpu = None
-    if rank == 0 and world == 1 and not args.no_reference_gpu:
-        del gs, e2e_step, draw_noise              # free the graph's pool before the reference allocates eagerly
+    # ------------------------------------------------ the other BASELINE configs + reference on this GPU (rank 0, N == 1) --
+    ref_gpu, others = None, None
+    if rank == 0 and world == 1 and not (args.no_reference_gpu and args.no_other_configs):
+        del gs, e2e_step, draw_noise              # free the graph's pool first
         torch.cuda.empty_cache()
-        ref_gpu = reference_gpu_record(args, value, e2e_value)
+        if not args.no_other_configs and args.nf == 64 and S == 256 and args.precision == 'bf16':
+            others = other_configs_record(args, dev)
+        if not args.no_reference_gpu:
+            ref_gpu = reference_gpu_record(args, value, e2e_value)
 
     # ------------------------------------------------ CPU baseline (rank 0, N == 1) -
     cpu = None
@@ -525,7 +590,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_replay * args.steps,
             "launches_per_step": launches_per_replay,
-            "roofline": roof, "cpu_baseline": cpu, "volume": vol, "reference_gpu": ref_gpu,
+            "roofline": roof, "cpu_baseline": cpu, "volume": vol, "reference_gpu": ref_gpu, "other_configs": others,
             "tensor_roofline_frac_end_to_end": e2e_frac,
         }
         print(json.dumps(line), flush=True)

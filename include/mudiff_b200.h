@@ -123,7 +123,8 @@ int mudiff_gn_scale_shift(const double* st0, int st0_ld, int c0, const double* s
                           const float* gamma, const float* beta, int64_t gb_bstride, int batch, int64_t hw,
                           int groups, float eps, float* table, void* stream);
 
-/* partial float[batch*tiles_per_image][n][2] (written by mudiff_conv_tc) -> chstats[b][st_off + c][2] */
+/* partial float[batch*rows_per_image][n][2] (written by mudiff_conv_tc: one row per pixel tile and TMEM lane quadrant,
+ * rows_per_image = 4 * tiles per image) -> chstats[b][st_off + c][2]; fixed summation order (deterministic) */
 int mudiff_stats_finalize(const float* partial, int tiles_per_image, int n, double* chstats, int st_ld,
                           int st_off, int batch, void* stream);
 int mudiff_gn_apply(const void* x0, int c0, int ld0, const double* st0, int st0_ld,

@@ -58,7 +58,7 @@ struct TcParams {
   const void* residual; int res_ld;
   float alpha, beta; int act;
   void* out; int out_ld, out_coff;
-  float* stats_partial;                       // [batch*tpi][n_total][2] or NULL
+  float* stats_partial;                       // [batch*tpi*4][n_total][2] (one row per image, tile, TMEM lane quadrant) or NULL
   // A-operand transform: y = act(x * scale[b][c] + shift[b][c]) applied to the staged tile of segment s
   const float* xform[3]; int xform_ld[3]; int xform_any, xform_act;
 };
@@ -258,7 +258,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], 4); }
     for (int i = 0; i < p.b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.MT); }     // one arrival per issuing warp
-    for (int i = 0; i < 32; ++i) ((int*)(bar_block + kDbgRecOff))[i] = 0;
+    for (int i = 0; i < 48; ++i) ((int*)(bar_block + kDbgRecOff))[i] = 0;      // progress records of up to 12 warps
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], p.MT); mbar_init(&tempty_bar[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -426,8 +426,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int et = (warp - 4) * 32 + lane;         // epilogue thread index 0..127
     const int row = q * 32 + lane;                 // accumulator row == pixel within the tile
     const int ty_in = row / p.tile_w, tx_in = row - ty_in * p.tile_w;
-    float* sstat = (float*)(smem + p.off_stats);   // [4 quadrants][n_tile][2]
-    float* sbias = sstat + 8 * p.n_tile;           // [n_tile] bias + row-bias of the current image
+    float* sbias = (float*)(smem + p.off_stats);   // [n_tile] bias + row-bias of the current image
     int bias_b = -1, bias_n0 = -1;
     int acc = 0; uint32_t acc_phase = 0;
     for (long long u = u_begin; u < u_end; u += u_step) {
@@ -541,28 +540,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             for (int j = 0; j < 32; ++j) f[j] = 0.f;
           }
           if (p.stats_partial) {
+            // per-channel (sum, sum^2) of this warp's 32 pixel rows: lane j ends up with the totals of column c + j and
+            // stores them straight to the partial buffer (row = (image, tile, lane quadrant)): no shared-memory staging,
+            // no named barrier; mudiff_stats_finalize adds the rows in a fixed order (deterministic, batch-invariant)
             float sq[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
             const float cs = warp_transpose_reduce(f, lane);
             const float cq = warp_transpose_reduce(sq, lane);
-            sstat[((q * p.n_tile) + c + lane) * 2 + 0] = cs;
-            sstat[((q * p.n_tile) + c + lane) * 2 + 1] = cq;
+            float* dst = p.stats_partial + (((((int64_t)un.b * p.tpi + r) * 4 + q) * p.n_total) + un.n0 + c + lane) * 2;
+            *reinterpret_cast<float2*>(dst) = make_float2(cs, cq);
           }
-        }
-        if (p.stats_partial) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          float* dst = p.stats_partial + (((int64_t)un.b * p.tpi + r) * p.n_total + un.n0) * 2;
-          for (int col = et; col < p.n_tile; col += 128) {
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              s0 += sstat[((w * p.n_tile) + col) * 2 + 0];
-              s1 += sstat[((w * p.n_tile) + col) * 2 + 1];
-            }
-            *reinterpret_cast<float2*>(dst + col * 2) = make_float2(s0, s1);
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
       dbg_mark(bar_block, -4, (int)(u - u_begin));
@@ -785,7 +773,7 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   p.total_units = (long long)d->batch * p.gpi * p.n_tiles;
   // shared memory plan
   const uint32_t bar_bytes = 1024;
-  const uint32_t stats_bytes = (uint32_t)n_tile * 36u;       // [4][n_tile][2] statistics staging + [n_tile] bias staging
+  const uint32_t stats_bytes = (uint32_t)n_tile * 4u;        // [n_tile] bias staging of the epilogue
   const uint32_t fixed = bar_bytes + ((stats_bytes + 1023u) & ~1023u) + 1024u /*alignment slack*/;
   const uint32_t avail = kSmemMax - fixed;
   const uint32_t b_total = (uint32_t)(ktot / 64) * p.b_sub_bytes;

@@ -230,20 +230,35 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const TI* __restrict__
 
 // Per-tile per-channel (sum, sumsq) float partials written by the conv epilogue -> per-channel doubles.
 // One block per image, ordered summation over the tiles (deterministic, batch-invariant).
-__global__ void stats_finalize_kernel(const float* __restrict__ partial, int tpi, int n, double* __restrict__ chstats,
-                                      int st_ld, int st_off) {
+// rows = partial rows per image (tiles x 4 lane quadrants).  Block (b, column block of 32): thread (col, seg) adds the rows
+// r = seg, seg + 32, ... of its column in order (8 independent loads in flight), the 32 segment sums are then added in
+// segment order in double precision: the order depends on `rows` only -> deterministic and batch-invariant.
+__global__ void __launch_bounds__(1024) stats_finalize_kernel(const float* __restrict__ partial, int rows, int n2,
+                                                              double* __restrict__ chstats, int st_ld, int st_off) {
+  __shared__ double red[32][33];
   const int b = blockIdx.x;
-  const float* pb = partial + (int64_t)b * tpi * n * 2;
-  for (int i = threadIdx.x; i < n * 2; i += blockDim.x) {
-    double a = 0.0;
-    int t = 0;
-    for (; t + 4 <= tpi; t += 4) {
-      const float v0 = pb[(int64_t)(t + 0) * n * 2 + i], v1 = pb[(int64_t)(t + 1) * n * 2 + i];
-      const float v2 = pb[(int64_t)(t + 2) * n * 2 + i], v3 = pb[(int64_t)(t + 3) * n * 2 + i];
-      a += (double)v0; a += (double)v1; a += (double)v2; a += (double)v3;
+  const int col = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int seg = threadIdx.x >> 5;
+  double a = 0.0;
+  if (col < n2) {
+    const float* pb = partial + (int64_t)b * rows * n2 + col;
+    int r = seg;
+    for (; r + 7 * 32 < rows; r += 8 * 32) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = pb[(int64_t)(r + 32 * i) * n2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a += (double)v[i];
     }
-    for (; t < tpi; ++t) a += (double)pb[(int64_t)t * n * 2 + i];
-    chstats[((int64_t)b * st_ld + st_off) * 2 + i] = a;
+    for (; r < rows; r += 32) a += (double)pb[(int64_t)r * n2];
+  }
+  red[seg][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (seg == 0 && col < n2) {
+    double t = 0.0;
+#pragma unroll 8
+    for (int s2 = 0; s2 < 32; ++s2) t += red[s2][threadIdx.x];
+    chstats[((int64_t)b * st_ld + st_off) * 2 + col] = t;
   }
 }
 
@@ -608,7 +623,7 @@ extern "C" int mudiff_gn_stats(const void* x, int c, int ld, int dtype, int batc
 extern "C" int mudiff_stats_finalize(const float* partial, int tiles_per_image, int n, double* chstats, int st_ld,
                                      int st_off, int batch, void* stream) {
   if (!partial || !chstats || tiles_per_image <= 0 || n <= 0 || batch <= 0 || st_ld < n + st_off) return MUDIFF_EINVAL;
-  stats_finalize_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(partial, tiles_per_image, n, chstats, st_ld, st_off);
+  stats_finalize_kernel<<<dim3(batch, (2 * n + 31) / 32), 1024, 0, (cudaStream_t)stream>>>(partial, tiles_per_image, 2 * n, chstats, st_ld, st_off);
   return mudiff_launch_status();
 }
 

@@ -375,7 +375,7 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
         q = (C.c_int32 * 10)()
         L.check(L.lib().mudiff_conv_tc_query(C.byref(d), q), 'conv_tc_query')
         tpi = q[2]
-        partial = torch.empty((b * tpi, n, 2), dtype=torch.float32, device=dev)
+        partial = torch.empty((b * tpi * 4, n, 2), dtype=torch.float32, device=dev)   # row = (image, tile, lane quadrant)
         d.stats = partial.data_ptr()
     prof = None
     if _PROFILER is not None:
@@ -402,7 +402,7 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
             else:
                 buf, off = stats_out
                 cs = buf[:, off:off + n]
-            L.check(L.lib().mudiff_stats_finalize(partial.data_ptr(), tpi, n, buf.data_ptr(), buf.shape[1], off, b, st),
+            L.check(L.lib().mudiff_stats_finalize(partial.data_ptr(), tpi * 4, n, buf.data_ptr(), buf.shape[1], off, b, st),
                     'stats_finalize')
         elif stats_out is not None or not (GN_SINGLE_PASS and region is out):
             cs = gn_stats(region, out=stats_out)
