@@ -61,6 +61,17 @@ int mudiff_upfirdn2d(const void* in, void* out, const float* kernel, int dtype,
                      int up_x, int up_y, int down_x, int down_y,
                      int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream);
 
+/* Both resampled branches of a resample ResnetBlockBigGANpp_Adagn (backbones/layerspp.py:293-305: h = act(AdaGN(x)),
+ * h = up/downsample_2d(h), x = up/downsample_2d(x)) from ONE read of x:
+ *   out_h = FIR(act(x * scale[b][c] + shift[b][c])),  out_x = FIR(x)
+ * x / out_h / out_x channels-last [batch, H, W, channels] dense, dtype MUDIFF_F32 | MUDIFF_BF16; kernel = the 4x4 fp32 FIR
+ * (gain folded in, as upfirdn2d gets it); table = float[batch][table_ld][2] from mudiff_gn_scale_shift;
+ * act MUDIFF_ACT_NONE | MUDIFF_ACT_SILU.  Modes: (up 2, down 1, pad 2/1) = upsample_2d, (up 1, down 2, pad 1/1) =
+ * downsample_2d (backbones/up_or_down_sampling.py:200-262); anything else MUDIFF_EUNSUPPORTED. */
+int mudiff_upfirdn2d_gn(const void* x, void* out_h, void* out_x, const float* kernel, const float* table,
+                        int table_ld, int act, int dtype, int batch, int in_h, int in_w, int channels,
+                        int up, int down, int pad0, int pad1, void* stream);
+
 /* Replaces fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
  * (utils/op/fused_bias_act.cpp:18-27, fused_bias_act_kernel.cu:20-51):
  *   x += bias[(i / step_b) % size_b] (if bias); act 1 = linear, 3 = leaky-relu(alpha);

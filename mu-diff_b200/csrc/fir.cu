@@ -261,6 +261,152 @@ int launch_fir4_quad(const void* in, void* out, const float* kern, const FirP& p
   return mudiff_launch_status();
 }
 
+// Fused AdaGN + SiLU + FIR for the resample ResBlocks (backbones/layerspp.py:293-305): h = act(AdaGN(x)) is FIR-resampled
+// and so is x itself - the reference runs GroupNorm, scale/shift, SiLU and two upfirdn2d calls, i.e. the full-resolution
+// normalised tensor is written and read back and x is read twice more.  Here ONE kernel reads x once and writes both
+// out_x = FIR(x) and out_h = FIR(act(x * scale[b][c] + shift[b][c])) with the folded AdaGN parameters of
+// mudiff_gn_scale_shift.  Zero padding applies AFTER the activation (taps outside the image contribute nothing to
+// either output).  Same geometry as fir4_quad_kernel (2x2 output quad per thread) with V = 4 channels per thread so that
+// the two accumulator sets fit in registers.
+template <typename T, int V> struct VecIO;
+template <> struct VecIO<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+    uint2 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+    h[0] = __floats2bfloat162_rn(v[0], v[1]); h[1] = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = raw;
+  }
+};
+template <> struct VecIO<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 r = *reinterpret_cast<const float4*>(p);
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <typename T, int UP, int DOWN, int YB>
+__global__ void __launch_bounds__(256, 2) fir4_quad_gn_kernel(const T* __restrict__ in, T* __restrict__ out_h, T* __restrict__ out_x,
+                                                           const float* __restrict__ kern, const float* __restrict__ table,
+                                                           int table_ld, int act, FirP p, int bxs, int bygs) {
+  using G = Fir4Geom<UP, DOWN>;
+  constexpr int V = 4;
+  constexpr int NR = G::NR;
+  __shared__ float sk[16];
+  if (threadIdx.x < 16) sk[threadIdx.x] = kern[15 - threadIdx.x];        // flipped: true convolution
+  __syncthreads();
+  float kf[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kf[i] = sk[i];
+  const int cv = p.minor / V;
+  const int64_t total = p.major * bygs * (int64_t)bxs * cv;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cv) * V;
+  int64_t r_ = idx / cv;
+  const int bx = (int)(r_ % bxs); r_ /= bxs;
+  const int byg = (int)(r_ % bygs);
+  const int64_t m = r_ / bygs;
+  float sc[V], sh[V];
+  {
+    const float* tp = table + ((int64_t)m * table_ld + c) * 2;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { sc[i] = tp[2 * i]; sh[i] = tp[2 * i + 1]; }
+  }
+  const T* inm = in + m * p.in_h * (int64_t)p.in_w * p.minor + c;
+  const int64_t obase = m * p.out_h * (int64_t)p.out_w * p.minor + c;
+  const int ox0 = bx * 2;
+  const int ix0 = UP == 2 ? (ox0 - p.px0) / 2 : ox0 * DOWN - p.px0;      // UP=2: px0 even -> exact
+#pragma unroll 1
+  for (int yb = 0; yb < YB; ++yb) {
+    const int oy0 = (byg * YB + yb) * 2;
+    if (oy0 >= p.out_h) break;
+    const int iy0 = UP == 2 ? (oy0 - p.py0) / 2 : oy0 * DOWN - p.py0;
+    float ax[2][2][V], ah[2][2][V];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int i = 0; i < V; ++i) { ax[a][b][i] = 0.f; ah[a][b][i] = 0.f; }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int iy = iy0 + r;
+      const bool oky = iy >= 0 && iy < p.in_h;
+      float xv[NR][V];
+      bool okx[NR];
+#pragma unroll
+      for (int s2 = 0; s2 < NR; ++s2) {
+        const int ix = ix0 + s2;
+        okx[s2] = oky && ix >= 0 && ix < p.in_w;
+#pragma unroll
+        for (int i = 0; i < V; ++i) xv[s2][i] = 0.f;
+        if (okx[s2]) VecIO<T, V>::load(inm + ((int64_t)iy * p.in_w + ix) * p.minor, xv[s2]);
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < NR; ++s2) {
+        float hv[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float t = fmaf(xv[s2][i], sc[i], sh[i]);
+          if (act == MUDIFF_ACT_SILU) t = (sizeof(T) == 4) ? silu_exact(t) : silu_f(t);
+          hv[i] = okx[s2] ? t : 0.f;
+        }
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const int ky = G::tap(dy, r);
+          if (ky < 0) continue;
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int kx = G::tap(dx, s2);
+            if (kx < 0) continue;
+            const float w = kf[ky * 4 + kx];
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              ax[dy][dx][i] = fmaf(w, xv[s2][i], ax[dy][dx][i]);
+              ah[dy][dx][i] = fmaf(w, hv[i], ah[dy][dx][i]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      if (oy0 + dy >= p.out_h) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        if (ox0 + dx >= p.out_w) continue;
+        const int64_t o = obase + ((int64_t)(oy0 + dy) * p.out_w + ox0 + dx) * p.minor;
+        VecIO<T, V>::store(out_x + o, ax[dy][dx]);
+        VecIO<T, V>::store(out_h + o, ah[dy][dx]);
+      }
+    }
+  }
+}
+
+template <typename T, int UP, int DOWN>
+int launch_fir4_quad_gn(const void* in, void* out_h, void* out_x, const float* kern, const float* table, int table_ld, int act,
+                        const FirP& p, cudaStream_t st) {
+  constexpr int V = 4, YB = 4;
+  const int cv = p.minor / V;
+  const int bxs = (p.out_w + 1) / 2;
+  const int bygs = ((p.out_h + 1) / 2 + YB - 1) / YB;
+  const int64_t total = p.major * bygs * (int64_t)bxs * cv;
+  const int64_t blocks = (total + 255) / 256;
+  if (blocks >= (1LL << 31)) return MUDIFF_EUNSUPPORTED;
+  fir4_quad_gn_kernel<T, UP, DOWN, YB><<<(unsigned)blocks, 256, 0, st>>>((const T*)in, (T*)out_h, (T*)out_x, kern, table, table_ld,
+                                                                     act, p, bxs, bygs);
+  return mudiff_launch_status();
+}
+
 template <typename T>
 int launch_fir(const void* in, void* out, const float* kern, const FirP& p, cudaStream_t st) {
   constexpr int V = 16 / sizeof(T);
@@ -321,4 +467,33 @@ extern "C" int mudiff_upfirdn2d(const void* in, void* out, const float* kernel, 
     case MUDIFF_F16: return launch_fir<__half>(in, out, kernel, p, st);
     default: return MUDIFF_EINVAL;
   }
+}
+
+// out_h = FIR(act(x * scale + shift)), out_x = FIR(x) from ONE read of x: the two resampled branches of a resample ResBlock
+// (backbones/layerspp.py:293-305).  x, out_h, out_x: channels-last [batch, H, W, C] dense; kernel: 4x4 fp32;
+// table: float[batch][table_ld][2] = (scale, shift) from mudiff_gn_scale_shift; act: MUDIFF_ACT_NONE | MUDIFF_ACT_SILU.
+// Only the generators' two modes: up = 2 with pad (2, 1) or down = 2 with pad (1, 1).
+extern "C" int mudiff_upfirdn2d_gn(const void* x, void* out_h, void* out_x, const float* kernel, const float* table,
+                                   int table_ld, int act, int dtype, int batch, int in_h, int in_w, int channels,
+                                   int up, int down, int pad0, int pad1, void* stream) {
+  if (!x || !out_h || !out_x || !kernel || !table || batch <= 0 || in_h <= 0 || in_w <= 0 || channels <= 0) return MUDIFF_EINVAL;
+  if (act != MUDIFF_ACT_NONE && act != MUDIFF_ACT_SILU) return MUDIFF_EINVAL;
+  if (!((up == 2 && down == 1 && pad0 == 2 && pad1 == 1) || (up == 1 && down == 2 && pad0 == 1 && pad1 == 1))) return MUDIFF_EUNSUPPORTED;
+  if (channels % 4 || table_ld < channels) return MUDIFF_EUNSUPPORTED;
+  if (((uintptr_t)x % 16) || ((uintptr_t)out_h % 16) || ((uintptr_t)out_x % 16)) return MUDIFF_EUNSUPPORTED;
+  FirP p;
+  p.major = batch; p.in_h = in_h; p.in_w = in_w; p.minor = channels; p.kh = 4; p.kw = 4;
+  p.up_x = p.up_y = up; p.down_x = p.down_y = down; p.px0 = p.py0 = pad0;
+  p.out_h = (in_h * up + pad0 + pad1 - 4) / down + 1;
+  p.out_w = (in_w * up + pad0 + pad1 - 4) / down + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MUDIFF_BF16) {
+    return up == 2 ? launch_fir4_quad_gn<__nv_bfloat16, 2, 1>(x, out_h, out_x, kernel, table, table_ld, act, p, st)
+                   : launch_fir4_quad_gn<__nv_bfloat16, 1, 2>(x, out_h, out_x, kernel, table, table_ld, act, p, st);
+  }
+  if (dtype == MUDIFF_F32) {
+    return up == 2 ? launch_fir4_quad_gn<float, 2, 1>(x, out_h, out_x, kernel, table, table_ld, act, p, st)
+                   : launch_fir4_quad_gn<float, 1, 2>(x, out_h, out_x, kernel, table, table_ld, act, p, st);
+  }
+  return MUDIFF_EUNSUPPORTED;
 }

@@ -285,10 +285,20 @@ class ResnetBlockBigGANpp_Adagn(nn.Module, layers.PackCache):
             h = ops.conv([(t, 9, (tab0, o)) for t, o in zip(xs, offs)], self.Conv_0.packed_weight(dt, seg_c), self.out_ch,
                          bias=self.Conv_0.bias_f32(), rowbias=tbias, want_stats=True)
         else:
-            h = self.GroupNorm_0(tuple(xs), zemb, act=L.ACT_SILU, gb=gb0)      # AdaGN + SiLU, one pass
-            if self.up or self.down:
-                h = self._resample(h)
-                xs = [self._resample(t) for t in xs]
+            fused = None
+            if (self.up or self.down) and self.fir and len(xs) == 1:
+                # AdaGN + SiLU + FIR of h AND the FIR of x from one read of x (layerspp.py:293-305): the full-resolution
+                # normalised tensor is never written
+                tab0 = self.GroupNorm_0.scale_shift(xs[0], zemb, gb=gb0)
+                fused = up_or_down_sampling.resample_2d_gn(xs[0], tab0, self.fir_kernel, up=self.up)
+            if fused is not None:
+                h, xr = fused
+                xs = [xr]
+            else:
+                h = self.GroupNorm_0(tuple(xs), zemb, act=L.ACT_SILU, gb=gb0)      # AdaGN + SiLU, one pass
+                if self.up or self.down:
+                    h = self._resample(h)
+                    xs = [self._resample(t) for t in xs]
             h = ops.conv([(h, 9)], self.Conv_0.packed_weight(dt), self.out_ch, bias=self.Conv_0.bias_f32(),
                          rowbias=tbias, want_stats=True)
         if fuse1:

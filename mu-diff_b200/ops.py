@@ -129,6 +129,33 @@ def upfirdn2d_nhwc(x, kernel_f32, up=1, down=1, pad=(0, 0)):
     return out
 
 
+FUSED_FIR_GN = _os.environ.get('MUDIFF_FUSED_FIR_GN', '1') != '0'
+
+
+def fir_resample_gn(x, table, kernel_f32, up: bool, act=L.ACT_SILU):
+    """(FIR(act(x * scale + shift)), FIR(x)) of a channels-last activation from ONE read of x: the two resampled
+    branches of a resample ResBlock (backbones/layerspp.py:293-305).  `table` = gn_scale_shift() output [B, C, 2];
+    `kernel_f32` the 4x4 device FIR kernel with the gain folded in; up=True: upsample_2d (x2), else downsample_2d (/2).
+    Returns None when the kernel does not take the shape (the caller then runs GroupNorm-apply + two FIR calls)."""
+    if not FUSED_FIR_GN or tuple(kernel_f32.shape) != (4, 4) or x.dtype not in (torch.bfloat16, torch.float32):
+        return None
+    L.require_cuda(x, table, kernel_f32)
+    x = as_nhwc(x)
+    b, c, h, w = x.shape
+    if _pix_ld(x) != c or c % 4:
+        return None
+    u, d, p0, p1 = (2, 1, 2, 1) if up else (1, 2, 1, 1)
+    oh, ow = (h * u + p0 + p1 - 4) // d + 1, (w * u + p0 + p1 - 4) // d + 1
+    out_h = empty_nhwc(b, c, oh, ow, x.dtype, x.device)
+    out_x = empty_nhwc(b, c, oh, ow, x.dtype, x.device)
+    rc = L.lib().mudiff_upfirdn2d_gn(x.data_ptr(), out_h.data_ptr(), out_x.data_ptr(), kernel_f32.data_ptr(), table.data_ptr(),
+                                     table.shape[1], act, L.dtype_code(x.dtype), b, h, w, c, u, d, p0, p1, L.stream_ptr(x.device))
+    if rc == L.EUNSUPPORTED:
+        return None
+    L.check(rc, 'upfirdn2d_gn')
+    return out_h, out_x
+
+
 # ---------------------------------------------------------------------------------
 # GroupNorm.  Statistics travel with the tensors as per-channel (sum, sumsq) doubles [B, C, 2]
 # (attribute `_mudiff_chstats`), produced by the conv epilogue or by the stand-alone stats kernel.

@@ -49,6 +49,18 @@ def downsample_2d(x, k=None, factor=2, gain=1):
     return _fir(x, k, down=factor, pad=((p + 1) // 2, p // 2))
 
 
+def resample_2d_gn(x, table, k=None, up=False, factor=2, gain=1):
+    """(upsample_2d | downsample_2d)(act(AdaGN(x))) AND the same resampling of x itself, fused (ops.fir_resample_gn);
+    kernel / gain / pads exactly as upsample_2d (:200-229) / downsample_2d (:232-262).  None if not applicable."""
+    if factor != 2 or (x.requires_grad and torch.is_grad_enabled()):
+        return None
+    kk = _setup_kernel([1] * factor if k is None else k) * (gain * (factor ** 2) if up else gain)
+    if kk.shape != (4, 4):
+        return None
+    kdev = ops.fir_kernel_device(np.ascontiguousarray(kk, dtype=np.float32), x.device)
+    return ops.fir_resample_gn(x, table, kdev, up)
+
+
 def naive_upsample_2d(x, factor=2):
     _N, C, H, W = x.shape
     k = np.ones((factor, factor), dtype=np.float32)          # nearest neighbour == zero-insert * ones

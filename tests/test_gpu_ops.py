@@ -661,3 +661,29 @@ def test_testset_driver_vs_reference_fixture(M, golden_dir, tmp_path):
         np.testing.assert_array_equal(g8, g[f'exp_{tag}_g8'])
         if tag != 'const':
             assert (np.float32(lo), np.float32(hi)) == tuple(np.float32(v) for v in g[f'exp_{tag}_win'])
+
+
+@pytest.mark.parametrize('up', [False, True])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape', [(2, 64, 32, 32), (3, 128, 18, 14), (1, 12, 7, 9)])
+def test_fused_adagn_silu_fir_resample(M, up, dtype, shape):
+    """mudiff_upfirdn2d_gn: (FIR(SiLU(x * scale + shift)), FIR(x)) from one read of x == the unfused sequence of the
+    reference's ResBlock (layerspp.py:293-305: AdaGN -> SiLU -> upsample_2d / downsample_2d on h and on x), computed
+    here in fp32 torch on the same (bf16-rounded) input with the reference's upfirdn2d_native restatement.  Odd sizes
+    check the window rows / columns outside the image (zero padding AFTER the activation)."""
+    from mudiff_b200 import ops, up_or_down_sampling as U
+    torch.manual_seed(3)
+    B, C, H, W = shape
+    x = torch.randn(B, C, H, W).to(dtype)
+    table = torch.stack([1.0 + 0.2 * torch.randn(B, C), 0.3 * torch.randn(B, C)], -1).contiguous()
+    got = U.resample_2d_gn(ops.as_nhwc(x.cuda()), table.cuda(), [1, 3, 3, 1], up=up)
+    assert got is not None
+    h, xr = got
+    xf = x.float()
+    act = F.silu(xf * table[:, :, 0, None, None] + table[:, :, 1, None, None])
+    res = (lambda t: O.upsample_2d(t, (1, 3, 3, 1), factor=2)) if up else (lambda t: O.downsample_2d(t, (1, 3, 3, 1), factor=2))
+    ref_h, ref_x = res(act), res(xf)
+    assert h.shape == ref_h.shape and xr.shape == ref_x.shape and h.dtype == dtype
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert (h.float().cpu() - ref_h).abs().max().item() <= tol * max(1.0, ref_h.abs().max().item())
+    assert (xr.float().cpu() - ref_x).abs().max().item() <= tol * max(1.0, ref_x.abs().max().item())
