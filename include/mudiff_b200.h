@@ -72,6 +72,13 @@ int mudiff_upfirdn2d_gn(const void* x, void* out_h, void* out_x, const float* ke
                         int table_ld, int act, int dtype, int batch, int in_h, int in_w, int channels,
                         int up, int down, int pad0, int pad1, void* stream);
 
+/* fp32 parity path on the tensor cores: x (fp32 channels-last, pixel stride ld) -> bf16 with x == hi + mid + lo exactly;
+ * layout 0: [pixels][3c] = (lo | mid | hi) (activation side), layout 1: [pixels][6c] = (lo | mid mid | hi hi hi) (the
+ * K-major "weight" side when that operand is an activation too: attention scores / PV / V^T).  The host then runs the
+ * tcgen05 conv on three channel-slice segments, small products first: [hi] x w_lo, [mid hi] x w_mid, [lo mid hi] x w_hi
+ * (the six products above 2^-24) with fp32 accumulation in TMEM. */
+int mudiff_split3_bf16(const float* x, int ld, void* out, int64_t pixels, int c, int layout, void* stream);
+
 /* Replaces fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
  * (utils/op/fused_bias_act.cpp:18-27, fused_bias_act_kernel.cu:20-51):
  *   x += bias[(i / step_b) % size_b] (if bias); act 1 = linear, 3 = leaky-relu(alpha);

@@ -47,6 +47,7 @@ PROTOTYPES = {
     'mudiff_conv_desc_size': [],
     'mudiff_upfirdn2d': [_P, _P, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'mudiff_upfirdn2d_gn': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'mudiff_split3_bf16': [_P, _I, _P, _L, _I, _I, _P],
     'mudiff_fused_bias_act': [_P, _P, _P, _P, _I, _L, _I, _L, _I, _I, _F, _F, _P],
     'mudiff_posterior_update': [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _P, _I, _L, _P],
     'mudiff_gn_stats': [_P, _I, _I, _I, _I, _L, _P, _I, _I, _P],

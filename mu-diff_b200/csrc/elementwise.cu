@@ -483,6 +483,59 @@ extern "C" int mudiff_add_scale(const void* a, const void* b, void* out, int dty
   DISPATCH3(dtype, launch_add_scale, a, b, out, n, scale, st);
 }
 
+// fp32 -> three bf16 planes (hi | mid | lo along the channel axis): x == hi + mid + lo exactly (24 mantissa bits = 3 x 8).
+// Feeds the tcgen05 conv on the fp32 parity path (ops.conv: six bf16 products per fp32 product, fp32 accumulation).
+// layout 0: [lo | mid | hi] (3c per pixel, the activation side); layout 1: [lo | mid mid | hi hi hi] (6c per pixel: the
+// "weight" side when the second operand is an activation too - attention scores / PV / V^T).  SMALL terms first: the conv
+// walks K in this order, so the products of relative size 2^-16 and 2^-8 are accumulated while the TMEM accumulator is
+// still small and the hi x hi products come last - the tensor core's fp32 accumulation truncates, and its error is
+// proportional to the accumulator's magnitude at every step.
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int ld, __nv_bfloat16* __restrict__ out,
+                                                    int64_t pixels, int c, int layout) {
+  const int cv = c / 8;
+  const int64_t total = pixels * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / cv;
+    const int c0 = (int)(i - pix * cv) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(x + pix * ld + c0);
+    const float4 b = *reinterpret_cast<const float4*>(x + pix * ld + c0 + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 hi, mid, lo;
+    __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(&hi);
+    __nv_bfloat16* pm = reinterpret_cast<__nv_bfloat16*>(&mid);
+    __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(&lo);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+      const float r1 = v[j] - __bfloat162float(h);
+      const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(m);
+      ph[j] = h; pm[j] = m; pl[j] = __float2bfloat16_rn(r2);
+    }
+    if (layout == 0) {
+      __nv_bfloat16* o = out + pix * (3 * (int64_t)c) + c0;
+      *reinterpret_cast<uint4*>(o) = lo;
+      *reinterpret_cast<uint4*>(o + c) = mid;
+      *reinterpret_cast<uint4*>(o + 2 * c) = hi;
+    } else {
+      __nv_bfloat16* o = out + pix * (6 * (int64_t)c) + c0;
+      *reinterpret_cast<uint4*>(o) = lo;
+      *reinterpret_cast<uint4*>(o + c) = mid;
+      *reinterpret_cast<uint4*>(o + 2 * c) = mid;
+      *reinterpret_cast<uint4*>(o + 3 * c) = hi;
+      *reinterpret_cast<uint4*>(o + 4 * c) = hi;
+      *reinterpret_cast<uint4*>(o + 5 * c) = hi;
+    }
+  }
+}
+
+extern "C" int mudiff_split3_bf16(const float* x, int ld, void* out, int64_t pixels, int c, int layout, void* stream) {
+  if (!x || !out || pixels <= 0 || c <= 0 || (layout != 0 && layout != 1)) return MUDIFF_EINVAL;
+  if (c % 8 || ld % 4 || ((uintptr_t)x % 16) || ((uintptr_t)out % 16)) return MUDIFF_EUNSUPPORTED;
+  split3_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(x, ld, (__nv_bfloat16*)out, pixels, c, layout);
+  return mudiff_launch_status();
+}
+
 extern "C" int mudiff_copy_channels(const void* src, int src_ld, int src_dtype, void* dst, int dst_ld, int dst_dtype,
                                     int64_t pixels, int c, void* stream) {
   if (pixels <= 0 || c <= 0) return pixels == 0 ? 0 : MUDIFF_EINVAL;

@@ -93,6 +93,7 @@ def refresh_packs(root: nn.Module) -> int:
         for key, entry in list(cache.items()):
             m._packed(key, entry[2], entry[3])
             n += 1
+    ops.refresh_split_weights()              # bf16 (hi | mid | lo) copies of packed fp32 weights (fp32 path on the tensor cores)
     return n
 
 

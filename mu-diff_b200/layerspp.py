@@ -307,6 +307,14 @@ class ResnetBlockBigGANpp_Adagn(nn.Module, layers.PackCache):
             hseg = (self.GroupNorm_1(h, zemb, act=L.ACT_SILU, gb=gb1), 9)
         sc = ops.SQRT2_INV if self.skip_rescale else 1.0
         w1 = self.Conv_1.packed_weight(dt)
+        if hasattr(self, 'Conv_2') and dt == torch.float32 and ops.FP32_TC and self.in_ch % 64 == 0 and self.out_ch % 64 == 0:
+            # fp32 path on the tensor cores (ops.conv splits a SINGLE fp32 segment into three bf16 ones): the shortcut is
+            # its own contraction and enters Conv_1's epilogue as the residual
+            c2 = self.Conv_2
+            xcat = xs[0] if len(xs) == 1 else ops.concat(xs)
+            short = ops.conv([(xcat, 1)], c2.packed_weight(dt), self.out_ch, bias=c2.bias_f32(), pad=0)
+            return ops.conv([hseg], w1, self.out_ch, bias=self.Conv_1.bias_f32(), residual=short, alpha=sc, beta=sc,
+                            want_stats=True)
         if hasattr(self, 'Conv_2'):
             # Conv_1(h) + Conv_2(x) as ONE contraction: K = 9*Cout + Cin   (layerspp.py:316-324)
             c2 = self.Conv_2

@@ -313,6 +313,81 @@ def pack_conv_weight(weight: torch.Tensor, seg_channels, dtype) -> torch.Tensor:
     return torch.cat(parts, dim=1).to(dtype).contiguous()
 
 
+# fp32 parity path on the tensor cores: every fp32 operand is split into three bf16 terms (x = hi + mid + lo exactly) and the
+# conv runs on the tcgen05 kernel as the six bf16 products above 2^-24, accumulated in fp32 (TMEM):
+#   [x_hi] * w_lo  +  [x_mid x_hi] * w_mid  +  [x_lo x_mid x_hi] * w_hi        (three channel-slice segments of ONE tensor
+#   [lo | mid | hi]; small products FIRST: the tensor core's fp32 accumulation truncates relative to the accumulator's
+#   magnitude, so the 2^-16 / 2^-8 terms are added while it is still small and hi x hi comes last)
+# 6x the bf16 FLOPs, still ~6x faster than the CUDA-core fp32 implicit GEMM.  MUDIFF_FP32_TC=0 restores the CUDA-core path.
+FP32_TC = _os.environ.get('MUDIFF_FP32_TC', '1') != '0'
+_split_w_cache = {}
+
+
+def split3(x):
+    """fp32 channels-last [B, C, H, W] -> bf16 [B, 3C, H, W] = (lo | mid | hi), x == hi + mid + lo."""
+    x = as_nhwc(x)
+    b, c, h, w = x.shape
+    out = empty_nhwc(b, 3 * c, h, w, torch.bfloat16, x.device)
+    L.check(L.lib().mudiff_split3_bf16(x.data_ptr(), _pix_ld(x), out.data_ptr(), b * h * w, c, 0, L.stream_ptr(x.device)), 'split3_bf16')
+    return out
+
+
+def split3_rows(wt, rows, k, ld):
+    """The K-major second operand when it is an fp32 ACTIVATION (`rows` rows of k values, row stride ld, e.g. the keys of
+    the attention scores): bf16 [rows, 6k] = (hi hi hi | mid mid | lo), matching the three segments of split3()."""
+    out = torch.empty((rows, 6 * k), dtype=torch.bfloat16, device=wt.device)
+    L.check(L.lib().mudiff_split3_bf16(wt.data_ptr(), ld, out.data_ptr(), rows, k, 1, L.stream_ptr(wt.device)), 'split3_bf16')
+    return out
+
+
+def _split3_weights_build(wt, c, taps):
+    n = wt.shape[0]
+    w = wt.detach().view(n, taps, c)
+    hi = w.to(torch.bfloat16)
+    r1 = w - hi.float()
+    mid = r1.to(torch.bfloat16)
+    lo = (r1 - mid.float()).to(torch.bfloat16)
+    return torch.cat([lo.reshape(n, -1), mid.unsqueeze(2).expand(n, taps, 2, c).reshape(n, -1),
+                      hi.unsqueeze(2).expand(n, taps, 3, c).reshape(n, -1)], dim=1).contiguous()
+
+
+def split3_weights(wt, c, taps):
+    """bf16 [N, taps * 6C] for the three segments above, cached per packed fp32 weight tensor; a changed weight is
+    re-split INTO the cached tensor (its address stays valid for captured graphs, see refresh_split_weights)."""
+    key = (wt.data_ptr(), tuple(wt.shape), taps, wt.device)
+    hit = _split_w_cache.get(key)
+    if hit is not None and hit[0] == wt._version:
+        return hit[1]
+    with torch.no_grad():
+        val = _split3_weights_build(wt, c, taps)
+        if hit is not None:
+            hit[1].copy_(val)
+            val = hit[1]
+    _split_w_cache[key] = (wt._version, val, wt, c)
+    return val
+
+
+def refresh_split_weights():
+    for key, (ver, val, wt, c) in list(_split_w_cache.items()):
+        if wt._version != ver:
+            split3_weights(wt, c, key[2])
+
+
+def fp32_tc_eligible(segs, n, stride, wt, w_bstride, w_ld, a_batched, batch, dec2) -> bool:
+    """One fp32 segment, stride 1, Cin % 64 == 0, N % 32 == 0.  Packed weights (w_bstride == 0) are split once and cached;
+    a per-sample / strided second operand (attention: w_bstride = N * w_ld) is split per call and must be 1-tap."""
+    if not FP32_TC or len(segs) != 1 or len(segs[0]) > 2 or stride != 1 or dec2 or n % 32:
+        return False
+    x, taps = segs[0][0], segs[0][1]
+    if x.dtype != torch.float32 or wt.dtype != torch.float32 or x.shape[1] % 64:
+        return False
+    k = taps * x.shape[1]
+    if w_bstride == 0 and w_ld == 0:
+        return a_batched and batch is None and wt.is_contiguous() and wt.ndim == 2 and wt.shape[1] == k
+    ld = w_ld or k
+    return taps == 1 and ld % 4 == 0 and (w_bstride == 0 or w_bstride == n * ld)
+
+
 def tc_eligible(segs, n, stride, dtype) -> bool:
     if dtype != torch.bfloat16 or stride != 1 or n % 32:
         return False
@@ -329,6 +404,19 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
     Chooses the tcgen05 kernel when eligible (bf16, Cin % 64 == 0, N % 32 == 0, stride 1), otherwise the
     CUDA-core kernel.  `force` in {None,'tc','simt'}."""
     x0 = segs[0][0]
+    if force is None and fp32_tc_eligible(segs, n, stride, wt, w_bstride, w_ld, a_batched, batch, dec2):
+        c, taps = x0.shape[1], segs[0][1]
+        x3 = split3(x0)
+        if w_bstride == 0 and w_ld == 0:
+            w3, wb3, wl3 = split3_weights(wt, c, taps), 0, 0
+        else:                                   # the second operand is an activation (attention): split it per call
+            nb = (batch if batch is not None else x0.shape[0]) if w_bstride else 1
+            w3 = split3_rows(wt, nb * n, c, w_ld or c)
+            wl3, wb3 = 6 * c, (n * 6 * c if w_bstride else 0)
+        return conv([(x3[:, 2 * c:], taps), (x3[:, c:], taps), (x3, taps)], w3, n, bias=bias,
+                    rowbias=rowbias, residual=residual, alpha=alpha, beta=beta, act=act, out=out, out_coff=out_coff,
+                    out_dtype=out_dtype or torch.float32, pad=pad, w_bstride=wb3, w_ld=wl3, a_batched=a_batched, batch=batch,
+                    flags=flags, force='tc', want_stats=want_stats, stats_out=stats_out, fused_stats=fused_stats)
     dev = x0.device
     b = batch if batch is not None else x0.shape[0]
     h, w = x0.shape[2], x0.shape[3]

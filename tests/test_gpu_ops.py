@@ -687,3 +687,32 @@ def test_fused_adagn_silu_fir_resample(M, up, dtype, shape):
     tol = 2e-5 if dtype == torch.float32 else 2e-2
     assert (h.float().cpu() - ref_h).abs().max().item() <= tol * max(1.0, ref_h.abs().max().item())
     assert (xr.float().cpu() - ref_x).abs().max().item() <= tol * max(1.0, ref_x.abs().max().item())
+
+
+@pytest.mark.parametrize('case', [dict(C=64, taps=9, N=64, B=2, H=32, W=32), dict(C=128, taps=9, N=256, B=1, H=24, W=20),
+                                  dict(C=256, taps=1, N=128, B=2, H=16, W=16)])
+def test_conv_fp32_on_tensor_cores(M, case):
+    """fp32 parity path on the tcgen05 kernel: x = hi + mid + lo (three bf16 terms, exact), six bf16 products, fp32
+    accumulation in TMEM, small products first (hi x hi last: the tensor core's accumulation truncates relative to the
+    accumulator's magnitude - with hi x hi first the error was 5e-6, in this order 4.5e-7).  Against F.conv2d in float64 the
+    error must be at fp32 level, <= 2e-6 of the output scale, for the tensor-core path and for the CUDA-core fp32 kernel."""
+    from mudiff_b200 import ops
+    torch.manual_seed(9)
+    C, taps, N, B, H, W = (case[k] for k in ('C', 'taps', 'N', 'B', 'H', 'W'))
+    k = 3 if taps == 9 else 1
+    x = torch.randn(B, C, H, W)
+    w = torch.randn(N, C, k, k) / (C * taps) ** 0.5
+    bias = torch.randn(N)
+    res = torch.randn(B, N, H, W)
+    ref = (0.7 * (F.conv2d(x.double(), w.double(), padding=k // 2) + bias.double()[None, :, None, None]) + 0.3 * res.double())
+    wt = ops.pack_conv_weight(w.cuda(), (C,), torch.float32)
+    kw = dict(bias=bias.cuda(), residual=ops.as_nhwc(res.cuda()), alpha=0.7, beta=0.3, pad=k // 2)
+    assert ops.fp32_tc_eligible([(ops.as_nhwc(x.cuda()), taps)], N, 1, wt, 0, 0, True, None, False)
+    y_tc = ops.conv([(ops.as_nhwc(x.cuda()), taps)], wt, N, **kw)
+    y_simt = ops.conv([(ops.as_nhwc(x.cuda()), taps)], wt, N, force='simt', **kw)
+    assert y_tc.dtype == torch.float32
+    scale = ref.abs().max().item()
+    e_tc = (y_tc.double().cpu() - ref).abs().max().item() / scale
+    e_simt = (y_simt.double().cpu() - ref).abs().max().item() / scale
+    print(f"[fp32 on tensor cores] C={C} taps={taps} N={N}: rel err tc={e_tc:.2e} simt={e_simt:.2e}")
+    assert e_tc <= 2e-6 and e_simt <= 2e-6
