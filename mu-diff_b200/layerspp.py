@@ -275,8 +275,11 @@ class ResnetBlockBigGANpp_Adagn(nn.Module, layers.PackCache):
         # (ops.conv xform) - the normalised tensor is then never stored.  Not across a FIR resample (the FIR reads
         # it), and only where it pays (ops.xform_profitable).
         tc_ok = dt == torch.bfloat16 and all(c % 64 == 0 for c in seg_c) and self.out_ch % 64 == 0
-        fuse0 = tc_ok and not (self.up or self.down) and ops.xform_profitable(seg_c)
-        fuse1 = tc_ok and ops.xform_profitable([self.out_ch], len(xs) if hasattr(self, 'Conv_2') else 0)
+        b_, _, h_, w_ = xs[0].shape
+        pix0 = b_ * h_ * w_
+        pix1 = pix0 * 4 if self.up else (pix0 // 4 if self.down else pix0)       # Conv_1 runs at the resampled resolution
+        fuse0 = tc_ok and not (self.up or self.down) and ops.xform_profitable(seg_c, pixels=pix0)
+        fuse1 = tc_ok and ops.xform_profitable([self.out_ch], len(xs) if hasattr(self, 'Conv_2') else 0, pixels=pix1)
         if tbias is None and temb is not None:
             tbias = ops.linear(temb, self.Dense_0.weight, self.Dense_0.bias, act_in=L.ACT_SILU)
         if fuse0:

@@ -222,13 +222,24 @@ def gn_apply(srcs, chstats, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-
 # write of every staged tile to shared-memory bandwidth that the N <= 128 tensor-core launches do not have to spare
 # (they are bound by the MMA operand reads): conv_tc +46 ms vs 48 ms of gn_apply saved per step when applied
 # everywhere, +5 ms vs 3 ms when restricted to single 64-channel segments (profiles/r01_fused_gn_ablation.md).
-#   MUDIFF_FUSED_GN = 0 (default) never, 1 single 64-channel 3x3 segment only, 2 wherever the kernel supports it
-FUSED_GN = int(_os.environ.get('MUDIFF_FUSED_GN', '0'))
+#   MUDIFF_FUSED_GN = auto (default): where the launch is small enough to be latency-bound rather than shared-memory-bound
+#                     (at most XFORM_MAX_PIXELS output pixels: every conv of a B <= 8 batch at 256^2, the 64^2 level of any
+#                     batch up to 128) - there the two HBM passes cost more than the transform (B = 1: 22.7 -> 19.3 ms per
+#                     sample, B = 4: +6.6 %, profiles/r02_small_batch.md);
+#                     0 never, 1 single 64-channel 3x3 segment only, 2 wherever the kernel supports it.
+# Fused and unfused paths are BIT-IDENTICAL (same fp32 scale / shift expressions, silu(t) = h + h tanh(h) on h = t / 2 with
+# the 1/2 folded into scale and shift exactly; tests/test_gpu_model.py::test_fused_groupnorm_is_bit_identical), so a
+# batch-size dependent choice does not break batch invariance.
+_fg = _os.environ.get('MUDIFF_FUSED_GN', 'auto')
+FUSED_GN = -1 if _fg == 'auto' else int(_fg)
+XFORM_MAX_PIXELS = int(_os.environ.get('MUDIFF_XFORM_MAX_PIXELS', str(8 * 65536)))
 
 
-def xform_profitable(seg_channels, extra_segments=0) -> bool:
+def xform_profitable(seg_channels, extra_segments=0, pixels=None) -> bool:
     if FUSED_GN >= 2:
         return True
+    if FUSED_GN < 0:
+        return pixels is not None and pixels <= XFORM_MAX_PIXELS
     return FUSED_GN == 1 and len(seg_channels) == 1 and seg_channels[0] == 64 and extra_segments == 0
 
 

@@ -480,3 +480,26 @@ def test_discriminator_vs_reference_golden(M, golden_dir, tag, ngf, temb, size, 
             assert el <= 1e-4 and em <= 1e-4, (el, em)
         else:
             assert rel <= 2e-2 and el <= 2e-2, (rel, el)
+
+
+def test_fused_groupnorm_is_bit_identical(M):
+    """The AdaGN + SiLU operand transform inside conv_tc (chosen per launch by size, ops.xform_profitable) must give
+    bit-identical results to the stand-alone GroupNorm-apply pass, otherwise a batch-size dependent choice would break
+    batch invariance (and with it the world-size independence of volume prediction)."""
+    from mudiff_b200 import ops
+    cfg = O.default_config(num_channels_dae=64, image_size=64)
+    ns, g1, g2, _, _ = _build(M, cfg, 'bf16')
+    conds, x_init, latents, noises = O.synthetic_inputs(3, 64, cfg, seed=11)
+    co = M.Posterior_Coefficients(ns, DEV)
+    c = _to(conds)
+    outs = {}
+    old = ops.FUSED_GN
+    try:
+        for mode in (0, 2, -1):
+            ops.FUSED_GN = mode
+            outs[mode] = M.sample_from_model(co, g1, c[0], g2, c[1], c[2], cfg.num_timesteps, x_init.to(DEV), None, ns,
+                                             latents=_to(latents), noises=_to(noises))
+    finally:
+        ops.FUSED_GN = old
+    assert torch.equal(outs[0], outs[2])
+    assert torch.equal(outs[0], outs[-1])
