@@ -499,8 +499,9 @@ __global__ void __launch_bounds__(256, 2) conv_stem_gn_kernel(SimtP p, const flo
     const float* r0 = y > 0 ? in + (int64_t)(y - 1) * W * ld : nullptr;
     const float* r1 = in + (int64_t)y * W * ld;
     const float* r2 = y + 1 < H ? in + (int64_t)(y + 1) * W * ld : nullptr;
-    for (int x = lane * 2; x < W; x += lanes * 2) {
-      float v[3][4];
+    // software pipeline: the 3x4 input window of the NEXT pixel pair is loaded before the current pair is computed (the
+    // kernel runs at 16 warps per SM - 110 registers of per-thread weights - so nothing else hides the load latency)
+    auto load_win = [&](float (&v)[3][4], int x) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int ix = x - 1 + c;
@@ -509,6 +510,19 @@ __global__ void __launch_bounds__(256, 2) conv_stem_gn_kernel(SimtP p, const flo
         v[1][c] = okx ? __ldg(r1 + (int64_t)ix * ld) : 0.f;
         v[2][c] = (okx && r2) ? __ldg(r2 + (int64_t)ix * ld) : 0.f;
       }
+    };
+    float v[3][4];
+    if (lane * 2 < W) load_win(v, lane * 2);
+    for (int x = lane * 2; x < W; x += lanes * 2) {
+      float vn[3][4];
+      if (x + lanes * 2 < W) load_win(vn, x + lanes * 2);
+      float xp[9][2];                            // taps of the two pixels, copied out so that v can be overwritten
+#pragma unroll
+      for (int t = 0; t < 9; ++t) { xp[t][0] = v[t / 3][t % 3]; xp[t][1] = v[t / 3][t % 3 + 1]; }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[r][c] = vn[r][c];
 #pragma unroll
       for (int px = 0; px < 2; ++px) {
         if (x + px >= W) break;
@@ -517,7 +531,7 @@ __global__ void __launch_bounds__(256, 2) conv_stem_gn_kernel(SimtP p, const flo
         for (int j = 0; j < 4; ++j) {
           f32x2 a = bs2[j];
 #pragma unroll
-          for (int t = 0; t < 9; ++t) { const float xv = v[t / 3][t % 3 + px]; a = fma2(pack2(xv, xv), w2[t][j], a); }
+          for (int t = 0; t < 9; ++t) { const float xv = xp[t][px]; a = fma2(pack2(xv, xv), w2[t][j], a); }
           unpack2(a, acc[2 * j], acc[2 * j + 1]);
         }
         if (p.act == MUDIFF_ACT_SILU) {
