@@ -22,6 +22,7 @@
 // Every mbarrier has exactly ONE in-order waiter role, and every wait is bounded (deadlock dump + trap).
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -852,6 +853,7 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
 
 #include "attn_tc.cuh"
 #include "stem_tc.cuh"
+#include "conv_tc2.cuh"
 
 }  // namespace
 
@@ -985,6 +987,31 @@ extern "C" int mudiff_conv_tc(const mudiff_conv_desc* d, void* stream) {
     int bh = p.seg_halo[ss] ? p.tile_h + 2 : p.tile_h;
     rc = make_map_a(&maps[s], d->a[ss], d->a_c[ss], d->a_ld[ss], d->w, d->h, d->a_batched ? d->batch : 1, bw, bh);
     if (rc) return rc;
+  }
+  // CTA-pair kernel (cta_group::2) for the shared-memory-bound N = 64 / 128 launches with stationary weights (conv_tc2.cuh).
+  // MUDIFF_CONV_PAIR=0 disables it.
+  static int pair_on = -1;
+  if (pair_on < 0) { const char* e = getenv("MUDIFF_CONV_PAIR"); pair_on = (e && e[0] == '0') ? 0 : 1; }
+  TcParams p2;
+  if (pair_on && !(d->flags & 0x4000) && plan_pair(d, p, ktot, p2)) {
+    rc = make_map_w(&mapw, d->wt, ktot, ktot, d->n, 1, 0, p2.n_tile / 2);
+    if (rc) return rc;
+    const size_t smem2 = (size_t)p2.off_bar + 1024 + 1024;
+    static bool attr2[16][2] = {};
+    int dev2 = 0; cudaGetDevice(&dev2);
+    if (dev2 < 0 || dev2 >= 16) return MUDIFF_EUNSUPPORTED;
+    const int w2 = d->out_dtype == MUDIFF_F32 ? 1 : 0;
+    if (!attr2[dev2][w2]) {
+      cudaError_t e = w2 ? cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)
+                         : cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+      if (e != cudaSuccess) return (int)e;
+      attr2[dev2][w2] = true;
+    }
+    long long pairs = p2.total_units < MUDIFF_NUM_SMS / 2 ? p2.total_units : MUDIFF_NUM_SMS / 2;
+    const int grid2 = (int)pairs * 2;
+    if (w2) conv_tc2_kernel<true><<<grid2, kThreads, smem2, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], mapw, p2);
+    else conv_tc2_kernel<false><<<grid2, kThreads, smem2, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], mapw, p2);
+    return mudiff_launch_status();
   }
   rc = make_map_w(&mapw, d->wt, ktot, d->w_ld > 0 ? d->w_ld : ktot, d->n, p.w_batched ? d->batch : 1, d->w_bstride, p.n_tile);
   if (rc) return rc;

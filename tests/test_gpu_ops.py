@@ -716,3 +716,53 @@ def test_conv_fp32_on_tensor_cores(M, case):
     e_simt = (y_simt.double().cpu() - ref).abs().max().item() / scale
     print(f"[fp32 on tensor cores] C={C} taps={taps} N={N}: rel err tc={e_tc:.2e} simt={e_simt:.2e}")
     assert e_tc <= 2e-6 and e_simt <= 2e-6
+
+
+PAIR_CASES = {
+    'n64_k576':       dict(C=[64], taps=[9], N=64, B=8, H=128, W=128),
+    'n64_shortcut':   dict(C=[64, 256], taps=[9, 1], N=64, B=8, H=128, W=128, epi=True),
+    'n64_k2304':      dict(C=[256], taps=[9], N=64, B=2, H=256, W=256),
+    'n128_k1152':     dict(C=[128], taps=[9], N=128, B=4, H=128, W=128, epi=True),
+    'n128_2src':      dict(C=[64, 64], taps=[9, 9], N=128, B=16, H=64, W=64, act=1),
+    'n64_f32out':     dict(C=[64], taps=[9], N=64, B=4, H=128, W=128, f32=True, epi=True),
+}
+
+
+@pytest.mark.parametrize('name', list(PAIR_CASES))
+def test_conv_tc_cta_pair_kernel(M, name):
+    """conv_tc2_kernel (cta_group::2: one UMMA 256 x N x 16 per CTA pair, weight rows split over the two CTAs) against the
+    fp32 reference AND against the single-CTA kernel (flag 0x4000 forces it) on the same inputs: same K order, fp32
+    accumulation in TMEM -> the two tensor-core kernels must agree bit for bit."""
+    from mudiff_b200 import ops
+    c = PAIR_CASES[name]
+    torch.manual_seed(21)
+    B, H, W, N = c['B'], c['H'], c['W'], c['N']
+    segs, segs_cpu, ws, wcpu = [], [], [], []
+    for ci, taps in zip(c['C'], c['taps']):
+        x = torch.randn(B, ci, H, W).to(torch.bfloat16)
+        k = 3 if taps == 9 else 1
+        w = (torch.randn(N, ci, k, k) / (ci * taps) ** 0.5).to(torch.bfloat16)
+        segs.append((ops.as_nhwc(x.cuda()), taps))
+        segs_cpu.append((x, taps))
+        ws.append(ops.pack_conv_weight(w.cuda(), (ci,), torch.bfloat16))
+        wcpu.append(w)
+    ref = _conv_ref(segs_cpu, wcpu)
+    kw = {}
+    if c.get('epi'):
+        bias, rowbias, res = torch.randn(N), torch.randn(B, N), torch.randn(B, N, H, W)
+        odt = torch.float32 if c.get('f32') else torch.bfloat16
+        resq = res.to(odt)
+        ref = 0.7 * (ref + bias[None, :, None, None] + rowbias[:, :, None, None]) + 0.3 * resq.float()
+        kw = dict(bias=bias.cuda(), rowbias=rowbias.cuda(), residual=ops.as_nhwc(resq.cuda()), alpha=0.7, beta=0.3)
+    if c.get('act') == 1:
+        ref = F.silu(ref)
+        kw['act'] = 1
+    wt = torch.cat(ws, dim=1).contiguous()
+    odt = torch.float32 if c.get('f32') else torch.bfloat16
+    out_pair = ops.conv(segs, wt, N, out_dtype=odt, force='tc', **kw)
+    out_single = ops.conv(segs, wt, N, out_dtype=odt, force='tc', flags=0x4000, **kw)
+    torch.cuda.synchronize()
+    scale = max(ref.abs().max().item(), 1.0)
+    tol = 2e-3 if odt == torch.float32 and not c.get('act') else 1.2e-2
+    assert (out_pair.float().cpu() - ref).abs().max().item() <= tol * scale
+    assert torch.equal(out_pair, out_single)

@@ -17,7 +17,9 @@ SHAPES = [  # (H, Cin list, taps, N)
     (64, [512], [9], 256),
     (256, [192], [9], 384),
 ]
-VARIANTS = [('default', 0), ('dry', 64), ('noepi', 128), ('dry+noepi', 192), ('mt1', 16), ('mt1+dry+noepi', 16 + 192), ('pertap', 2)]
+VARIANTS = [('default', 0), ('pair+dry', 64), ('pair+noepi', 128), ('pair+dry+noepi', 192), ('single', 0x4000), ('single+nostore', 0x4000 + 2048), ('single+noldtm', 0x4000 + 4096), ('single+noepi', 0x4000 + 128), ('single+dry', 0x4000 + 64), ('single+dry+noepi', 0x4000 + 192), ('single+mt1', 0x4000 + 16)]
+if os.environ.get('CB_SHAPES'):
+    SHAPES = [SHAPES[int(i)] for i in os.environ['CB_SHAPES'].split(',')]
 
 
 def bench(fn, iters=5):
@@ -43,7 +45,7 @@ for H, cins, taps, N in SHAPES:
     out = ops.empty_nhwc(B, N, H, H, torch.bfloat16, 'cuda')
     line = f"H={H:3d} Cin={cins} N={N:3d} K={ktot:5d}: "
     for name, fl in VARIANTS:
-        for st in ((0, 1) if name in ('default', 'dry') and N <= 256 else (0,)):
+        for st in (0,):
             try:
                 ms = bench(lambda: ops.conv(segs, wt, N, out=out, flags=fl, force='tc', want_stats=bool(st)))
                 line += f"{name}{'+stats' if st else ''}={flops / ms / 1e9:6.0f}  "
