@@ -235,6 +235,93 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
+// Epilogue arithmetic of one 32-column chunk of one accumulator row (shared by conv_tc_kernel and conv_tc2_kernel, so that the
+// two kernels stay bit-identical): f = (acc + bias) * alpha [+ beta * residual] -> activation -> bf16 | fp32 store.
+// Packed fp32x2 instructions (add / mul / fma on register pairs): half the issue slots of the scalar form, identical rounding.
+// On return f[] holds the values as stored (bf16-rounded for bf16 outputs) for the optional statistics.
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+template <bool kOutF32>
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], float (&f)[32], const float* sbias_c,
+                                               int64_t pix, int n, bool want_rounded) {
+  f32x2 t[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t[j] = pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+  if (p.bias || p.rowbias) {
+    const float4* sb4 = reinterpret_cast<const float4*>(sbias_c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 bv = sb4[j];
+      t[2 * j] = add2(t[2 * j], pack2(bv.x, bv.y));
+      t[2 * j + 1] = add2(t[2 * j + 1], pack2(bv.z, bv.w));
+    }
+  }
+  const f32x2 al2 = pack2(p.alpha, p.alpha);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t[j] = mul2(t[j], al2);
+  if (p.residual) {
+    const f32x2 be2 = pack2(p.beta, p.beta);
+    if (kOutF32) {
+      const float4* rp = reinterpret_cast<const float4*>((const float*)p.residual + pix * p.res_ld + n);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 rv = rp[j];
+        t[2 * j] = fma2(be2, pack2(rv.x, rv.y), t[2 * j]);
+        t[2 * j + 1] = fma2(be2, pack2(rv.z, rv.w), t[2 * j + 1]);
+      }
+    } else {
+      const uint4* rp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.residual + pix * p.res_ld + n);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 raw = rp[j];
+        const __nv_bfloat162* e = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 r2 = __bfloat1622float2(e[i]);
+          t[4 * j + i] = fma2(be2, pack2(r2.x, r2.y), t[4 * j + i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) unpack2(t[j], f[2 * j], f[2 * j + 1]);
+  if (p.act == MUDIFF_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = sigmoid_f(f[j]);
+  } else if (p.act == MUDIFF_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+  } else if (p.act == MUDIFF_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+  } else if (p.act == MUDIFF_ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
+  }
+  if (kOutF32) {
+    float4* op = reinterpret_cast<float4*>((float*)p.out + pix * p.out_ld + p.out_coff + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  } else {
+    uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)p.out + pix * p.out_ld + p.out_coff + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 raw;
+      __nv_bfloat162* e = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) e[i] = __floats2bfloat162_rn(f[8 * j + 2 * i], f[8 * j + 2 * i + 1]);
+      op[j] = raw;
+      if (want_rounded) {             // statistics of what was actually stored (bf16-rounded)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 rr = __bfloat1622float2(e[i]);
+          f[8 * j + 2 * i] = rr.x; f[8 * j + 2 * i + 1] = rr.y;
+        }
+      }
+    }
+  }
+}
+
 template <bool kOutF32>
 __global__ void __launch_bounds__(kThreadsXform, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -468,74 +555,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           const int n = un.n0 + c;
           float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (valid && !p.dbg_nostore) {
-            if (p.bias || p.rowbias) {
-              const float4* sb4 = reinterpret_cast<const float4*>(sbias + c);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bv = sb4[j];
-                f[4 * j + 0] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
-            if (p.residual) {
-              if (kOutF32) {
-                const float4* rp = reinterpret_cast<const float4*>((const float*)p.residual + pix * p.res_ld + n);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float4 rv = rp[j];
-                  f[4 * j + 0] = fmaf(p.beta, rv.x, f[4 * j + 0]); f[4 * j + 1] = fmaf(p.beta, rv.y, f[4 * j + 1]);
-                  f[4 * j + 2] = fmaf(p.beta, rv.z, f[4 * j + 2]); f[4 * j + 3] = fmaf(p.beta, rv.w, f[4 * j + 3]);
-                }
-              } else {
-                const uint4* rp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.residual + pix * p.res_ld + n);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  uint4 raw = rp[j];
-                  const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[8 * j + i] = fmaf(p.beta, __bfloat162float(e[i]), f[8 * j + i]);
-                }
-              }
-            }
-            if (p.act == MUDIFF_ACT_SIGMOID) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = sigmoid_f(f[j]);
-            } else if (p.act == MUDIFF_ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
-            } else if (p.act == MUDIFF_ACT_TANH) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
-            } else if (p.act == MUDIFF_ACT_LRELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
-            }
-            if (kOutF32) {
-              float4* op = reinterpret_cast<float4*>((float*)p.out + pix * p.out_ld + p.out_coff + n);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            } else {
-              uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)p.out + pix * p.out_ld + p.out_coff + n);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 raw;
-                __nv_bfloat162* e = reinterpret_cast<__nv_bfloat162*>(&raw);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) e[i] = __floats2bfloat162_rn(f[8 * j + 2 * i], f[8 * j + 2 * i + 1]);
-                op[j] = raw;
-                if (p.stats_partial) {          // statistics of what was actually stored (bf16-rounded)
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float2 rr = __bfloat1622float2(e[i]);
-                    f[8 * j + 2 * i] = rr.x; f[8 * j + 2 * i + 1] = rr.y;
-                  }
-                }
-              }
-            }
+            epilogue_chunk<kOutF32>(p, v, f, sbias + c, pix, n, p.stats_partial != nullptr);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = 0.f;

@@ -19,7 +19,10 @@
 //               Four accumulator stages (4 x N TMEM columns) decouple the MMA stream from the hand-over latency.
 // Every mbarrier keeps exactly one in-order waiter role per CTA.  Restrictions (the host falls back to conv_tc_kernel otherwise):
 // stationary weights, one N tile (N = 64 or 128), even number of pixel tiles per image, no operand transform, no fused
-// statistics, no decimation.
+// statistics, no decimation.  (A streamed-weight variant - ring of half sub-tiles completing on the leader's barrier - was
+// built and is correct, but with ONE issuing thread per pair the per-tap wait + commit makes it slower than the single-CTA
+// kernel with its two issuers: N = 64, K = 2880: 23.3 vs 13.2 ms; and the extra branches in the issue loop cost the
+// stationary launches 20-35 %.  Those launches stay on conv_tc_kernel.)
 
 constexpr int kPairStagesMax = 8;
 
@@ -238,68 +241,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           tmem_ld32(taddr0 + (uint32_t)c, v);
           tmem_ld_wait();
           float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (valid) {
-            if (p.bias || p.rowbias) {
-              const float4* sb4 = reinterpret_cast<const float4*>(sbias + c);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bv = sb4[j];
-                f[4 * j + 0] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
-            if (p.residual) {
-              if (kOutF32) {
-                const float4* rp = reinterpret_cast<const float4*>((const float*)p.residual + pix * p.res_ld + c);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 rv = rp[j];
-                  f[4 * j + 0] = fmaf(p.beta, rv.x, f[4 * j + 0]); f[4 * j + 1] = fmaf(p.beta, rv.y, f[4 * j + 1]);
-                  f[4 * j + 2] = fmaf(p.beta, rv.z, f[4 * j + 2]); f[4 * j + 3] = fmaf(p.beta, rv.w, f[4 * j + 3]);
-                }
-              } else {
-                const uint4* rp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)p.residual + pix * p.res_ld + c);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 raw = rp[j];
-                  const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[8 * j + i] = fmaf(p.beta, __bfloat162float(e[i]), f[8 * j + i]);
-                }
-              }
-            }
-            if (p.act == MUDIFF_ACT_SIGMOID) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = sigmoid_f(f[j]);
-            } else if (p.act == MUDIFF_ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
-            } else if (p.act == MUDIFF_ACT_TANH) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
-            } else if (p.act == MUDIFF_ACT_LRELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
-            }
-            if (kOutF32) {
-              float4* op = reinterpret_cast<float4*>((float*)p.out + pix * p.out_ld + p.out_coff + c);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            } else {
-              uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)p.out + pix * p.out_ld + p.out_coff + c);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 raw;
-                __nv_bfloat162* e = reinterpret_cast<__nv_bfloat162*>(&raw);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) e[i] = __floats2bfloat162_rn(f[8 * j + 2 * i], f[8 * j + 2 * i + 1]);
-                op[j] = raw;
-              }
-            }
-          }
+          if (valid) epilogue_chunk<kOutF32>(p, v, f, sbias + c, pix, c, false);
         }
       }
       tc_fence_before();
@@ -340,7 +282,9 @@ static bool plan_pair(const mudiff_conv_desc* d, const TcParams& p1, int ktot, T
   const uint32_t bar_bytes = 1024, stats_bytes = (uint32_t)p.n_tile * 4u;
   const uint32_t fixed = bar_bytes + ((stats_bytes + 1023u) & ~1023u) + 1024u;
   const uint32_t b_total = (uint32_t)p.b_total_subs * p.b_sub_bytes;
-  if (b_total + 3u * p.a_slot_bytes + fixed > kSmemMax) return false;
+  static int min_slots = 0;
+  if (!min_slots) { const char* e = getenv("MUDIFF_PAIR_MIN_SLOTS"); min_slots = e ? atoi(e) : 3; if (min_slots < 2) min_slots = 2; }
+  if (b_total + (uint32_t)min_slots * p.a_slot_bytes + fixed > kSmemMax) return false;
   int as = (int)((kSmemMax - fixed - b_total) / p.a_slot_bytes);
   p.a_slots = as > 8 ? 8 : as;
   p.a_ring = p.a_slots;
