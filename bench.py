@@ -54,11 +54,12 @@ def peaks():
 
 def ncu_traffic():
     """Mean dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch, over ALL conv_tc launches of one step of
-    this workload (B = 64, 256^2), from the committed ncu capture profiles/r01_conv_tc_dram.csv (tools/profile_r01.sh).
+    this workload (B = 64, 256^2), from the committed ncu capture profiles/r02_conv_tc_dram.csv (tools/profile_r02.sh;
+    conv_tc_kernel and the CTA-pair conv_tc2_kernel).
     None if the capture is not there."""
     import csv
     import gzip
-    p = os.path.join(ROOT, 'profiles', 'r01_conv_tc_dram.csv')
+    p = os.path.join(ROOT, 'profiles', 'r02_conv_tc_dram.csv')
     if not os.path.exists(p) and os.path.exists(p + '.gz'):
         p += '.gz'
     if not os.path.exists(p):
@@ -79,7 +80,7 @@ def ncu_traffic():
     if not per:
         return None, "capture has no dram__bytes rows"
     return sum(per.values()) / len(per), (f"mean DRAM bytes (read + write) per conv_tc launch over the {len(per)} conv_tc launches "
-                                          "of one eager step of this workload, ncu capture profiles/r01_conv_tc_dram.csv")
+                                          "of one eager step of this workload, ncu capture profiles/r02_conv_tc_dram.csv")
 
 
 class ClockSampler(threading.Thread):
@@ -542,7 +543,7 @@ def main():
         simt_ms = sum(r.a.elapsed_time(r.b) for r in recs if r.kind == 'conv_simt')
         ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         traffic, traffic_note = ncu_traffic()
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "achieved": ach,
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel + conv_tc2_kernel (tcgen05 implicit-GEMM conv: single CTA and cta_group::2 CTA pair)", "achieved": ach,
                 "peak": pk['tf_sustained'], "unit": "TFLOP/s", "frac": ach / pk['tf_sustained'], "traffic": traffic,
                 "traffic_note": traffic_note,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",

@@ -9,8 +9,8 @@ export MUDIFF_WAIT_CYCLES=0
 B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-roofline --no-volume --no-reference-gpu --no-other-configs"
 $B > $O/plain.json 2> $O/plain.err || { echo "plain bench failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/launches.csv $B > $O/ncu1.log 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_tc_kernel -c 420 --csv --log-file $O/conv_tc_dram.csv $B > $O/ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel|gn_apply_kernel|gn_stats_kernel|fir4_quad|conv_stem_gn|conv_head|attn_tc" -c 36 -o $O/full_a -f $B > $O/ncu3.log 2>&1
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_tc -c 420 --csv --log-file $O/conv_tc_dram.csv $B > $O/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"conv_tc|gn_apply_kernel|gn_stats_kernel|fir4_quad|conv_stem_gn|conv_head|attn_tc" -c 40 -o $O/full_a -f $B > $O/ncu3.log 2>&1
 ncu -i $O/full_a.ncu-rep --page raw --csv > $O/full_a_raw.csv 2>/dev/null
 B1="python bench.py --batch 1 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-roofline --no-volume --no-reference-gpu --no-other-configs"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/launches_b1.csv $B1 > $O/ncu5.log 2>&1
