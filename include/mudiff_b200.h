@@ -145,6 +145,15 @@ int mudiff_gn_scale_shift(const double* st0, int st0_ld, int c0, const double* s
  * rows_per_image = 4 * tiles per image) -> chstats[b][st_off + c][2]; fixed summation order (deterministic) */
 int mudiff_stats_finalize(const float* partial, int tiles_per_image, int n, double* chstats, int st_ld,
                           int st_off, int batch, void* stream);
+/* mudiff_gn_stats(x0) + mudiff_gn_apply([x0 | x1]) in ONE launch (AdaptiveGroupNorm + SiLU, backbones/layerspp.py:47-54,
+ * 293, 314): every block re-reads its own 64 KB chunk from L2 after the image's statistics are complete, so the tensor crosses
+ * HBM twice (read, write) instead of three times.  st0 receives x0's per-channel (sum, sumsq); x1 / st1 (optional) is the
+ * channel-concat partner with known statistics.  bf16 only; bit-identical to the two-call sequence; MUDIFF_EUNSUPPORTED
+ * when the shape does not qualify. */
+int mudiff_gn_stats_apply(const void* x0, int c0, int ld0, double* st0, int st0_ld,
+                          const void* x1, int c1, int ld1, const double* st1, int st1_ld, int dtype,
+                          const float* gamma, const float* beta, int64_t gb_bstride,
+                          void* out, int ld_out, int batch, int64_t hw, int groups, float eps, int act, void* stream);
 int mudiff_gn_apply(const void* x0, int c0, int ld0, const double* st0, int st0_ld,
                     const void* x1, int c1, int ld1, const double* st1, int st1_ld, int dtype_in,
                     const float* gamma, const float* beta, int64_t gb_bstride,

@@ -54,6 +54,7 @@ PROTOTYPES = {
     'mudiff_gn_fused': [_P, _P, _I, _I, _L, _I, _P, _P, _L, _F, _I, _P, _I, _I, _P],
     'mudiff_gn_scale_shift': [_P, _I, _I, _P, _I, _I, _P, _P, _L, _I, _L, _I, _F, _P, _P],
     'mudiff_stats_finalize': [_P, _I, _I, _P, _I, _I, _I, _P],
+    'mudiff_gn_stats_apply': [_P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _I, _I, _L, _I, _F, _I, _P],
     'mudiff_gn_apply': [_P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _I, _I, _I, _L, _I, _F, _I, _P],
     'mudiff_zero': [_P, _L, _P],
     'mudiff_conv_tc': [C.POINTER(ConvDesc), _P],

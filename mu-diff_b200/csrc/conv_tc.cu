@@ -751,7 +751,10 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   p.batch = d->batch; p.H = d->h; p.W = d->w;
   int n_tile = 0;
   for (int c = 256; c >= 32; c -= 32) if (d->n % c == 0) { n_tile = c; break; }
-  if (!n_tile) return MUDIFF_EUNSUPPORTED;
+  // N tiles between 128 and 256 columns (N = 384 -> 192) leave room for ONE accumulator stage only (2 tiles x 256 TMEM columns):
+  // the epilogue is then not overlapped with the next unit's MMAs (tools/conv_bench.py, N = 384, K = 1728: 1243 TFLOP/s, 1755
+  // without the epilogue).  128-column tiles keep two stages: gate conv 20.3 -> 15.6 ms per bench step.  Flag 0x400000: old plan.
+  if (!(d->flags & 0x400000) && n_tile > 128 && n_tile < 256 && d->n % 128 == 0) n_tile = 128;
   p.n_tile = n_tile; p.n_tiles = d->n / n_tile; p.n_total = d->n;
   // A staging: halo whenever a 3x3 segment exists and the image is at least one 8x2 patch
   bool halo = any9 && d->w >= 8 && d->h >= 2 && !(d->flags & 2);

@@ -5,6 +5,7 @@
 //     (only taps that hit a non-inserted sample are visited), fully coalesced;
 //   * NCHW (minor == 1): shared-memory staged input tile + flipped taps, 32x32 output tile;
 //   * anything else: generic per-element gather.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -407,6 +408,221 @@ int launch_fir4_quad_gn(const void* in, void* out_h, void* out_x, const float* k
   return mudiff_launch_status();
 }
 
+// Shared-memory tiled variant of the fused AdaGN + SiLU + FIR kernel (bf16, channels % 32 == 0): the register-window kernel above
+// evaluates the activation once per WINDOW position (2.25x per input element when downsampling, 9x when upsampling) and
+// re-reads every input 2.25 / 9 times through L1, which left it MUFU / LSU bound at a third of the HBM roofline.  Here a CTA
+// stages the input tile (+ FIR halo) of a 32-channel chunk ONCE: raw x and h = act(x * scale + shift) rounded to bf16 (exactly
+// what the stand-alone GroupNorm pass stores), then every thread filters 2 (down) / 2 x 4 (up) outputs of one 16-byte channel
+// vector from shared memory.  DOWN: 8 x 16 outputs from 18 x 34 inputs (76.5 KB, two CTAs per SM; pixel slots swizzled so
+// that the stride-2 window reads are bank-conflict free); UP: 16 x 32 outputs from 10 x 18 inputs.
+constexpr int kFirCC = 32;
+template <int UP, int DOWN> struct FirTile {
+  static constexpr int OTH = DOWN == 2 ? 8 : 16, OTW = DOWN == 2 ? 16 : 32;
+  static constexpr int ITH = DOWN == 2 ? 18 : 10, ITW = DOWN == 2 ? 34 : 18;
+  static constexpr int SMEM = ITH * ITW * (kFirCC * 2) * 2;
+  static __device__ __forceinline__ int slot(int q) { return DOWN == 2 ? (q ^ ((q >> 1) & 1)) : q; }
+};
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& raw, f32x2 (&v)[4]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[i] = pack2(f.x, f.y); }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const f32x2 (&v)[4]) {
+  uint4 raw;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float a, b; unpack2(v[i], a, b); h[i] = __floats2bfloat162_rn(a, b); }
+  return raw;
+}
+
+template <int UP, int DOWN>
+__global__ void __launch_bounds__(256, 2) fir4_tile_gn_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out_h,
+                                                           __nv_bfloat16* __restrict__ out_x, const float* __restrict__ kern,
+                                                           const float* __restrict__ table, int table_ld, int act, FirP p,
+                                                           int tiles_x, int tiles_y, int cchunks) {
+  using G = Fir4Geom<UP, DOWN>;
+  using TL = FirTile<UP, DOWN>;
+  extern __shared__ uint4 fir_smem[];
+  uint4* sx = fir_smem;                                   // [ITH * ITW pixel slots][4 vectors] raw x
+  uint4* sh = fir_smem + TL::ITH * TL::ITW * 4;           // ... activated, bf16-rounded
+  __shared__ float sk[16];
+  if (threadIdx.x < 16) sk[threadIdx.x] = kern[15 - threadIdx.x];        // flipped: true convolution
+  int bid = blockIdx.x;
+  const int cc = bid % cchunks; bid /= cchunks;
+  const int tx = bid % tiles_x; bid /= tiles_x;
+  const int ty = bid % tiles_y;
+  const int64_t m = bid / tiles_y;
+  const int oy0 = ty * TL::OTH, ox0 = tx * TL::OTW;
+  const int iy0 = UP == 2 ? (oy0 - p.py0) / 2 : oy0 * DOWN - p.py0;     // UP: oy0, py0 even -> exact
+  const int ix0 = UP == 2 ? (ox0 - p.px0) / 2 : ox0 * DOWN - p.px0;
+  const int v = threadIdx.x & 3;
+  const int c0 = cc * kFirCC + v * 8;
+  {
+    // ---- stage: one 16-byte vector per thread per trip; (scale, shift) of this thread's 8 channels live in registers
+    f32x2 sc[4], sf[4];
+    const float4* tp = reinterpret_cast<const float4*>(table + ((int64_t)m * table_ld + c0) * 2);
+    const float hf = act == MUDIFF_ACT_SILU ? 0.5f : 1.f;             // silu(t) = h + h tanh(h), h = t / 2
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t4 = __ldg(tp + i);
+      sc[i] = pack2(t4.x * hf, t4.z * hf); sf[i] = pack2(t4.y * hf, t4.w * hf);
+    }
+    const __nv_bfloat16* inm = in + m * p.in_h * (int64_t)p.in_w * p.minor + c0;
+    constexpr int ITEMS = TL::ITH * TL::ITW * 4;
+    constexpr int TRIPS = (ITEMS + 255) / 256;
+    uint4 raw[TRIPS];
+    bool ok[TRIPS];
+#pragma unroll
+    for (int j = 0; j < TRIPS; ++j) {
+      const int it = threadIdx.x + 256 * j;
+      const int q = it >> 2;
+      const int r = q / TL::ITW, c = q - r * TL::ITW;
+      const int iy = iy0 + r, ix = ix0 + c;
+      ok[j] = it < ITEMS && iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w;
+      raw[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok[j]) raw[j] = __ldg(reinterpret_cast<const uint4*>(inm + ((int64_t)iy * p.in_w + ix) * p.minor));
+    }
+#pragma unroll
+    for (int j = 0; j < TRIPS; ++j) {
+      const int it = threadIdx.x + 256 * j;
+      if (it < ITEMS) {
+        uint4 hv = make_uint4(0u, 0u, 0u, 0u);
+        if (ok[j]) {                                                  // zero padding applies AFTER the activation
+          f32x2 x2[4];
+          unpack_bf16x8(raw[j], x2);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            x2[i] = fma2(x2[i], sc[i], sf[i]);
+            if (act == MUDIFF_ACT_SILU) {
+              float a, b; unpack2(x2[i], a, b);
+              x2[i] = fma2(x2[i], pack2(tanh_approx(a), tanh_approx(b)), x2[i]);
+            }
+          }
+          hv = pack_bf16x8(x2);
+        }
+        const int s = TL::slot(it >> 2) * 4 + v;
+        sx[s] = raw[j]; sh[s] = hv;
+      }
+    }
+  }
+  __syncthreads();
+  float kf[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kf[i] = sk[i];
+  const int64_t obase = m * p.out_h * (int64_t)p.out_w * p.minor + c0;
+  if (DOWN == 2) {
+    // ---- one vertical pair of outputs per thread: window rows 4 * oyp .. + 5, columns 2 * ox .. + 3 of the staged tile
+    const int ox = (threadIdx.x >> 2) & 15, oyp = threadIdx.x >> 6;
+    f32x2 ax[2][4], ah[2][4];
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { ax[d][i] = pack2(0.f, 0.f); ah[d][i] = pack2(0.f, 0.f); }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int s = TL::slot((4 * oyp + r) * TL::ITW + 2 * ox + c) * 4 + v;
+        f32x2 xv[4], hv[4];
+        unpack_bf16x8(sx[s], xv);
+        unpack_bf16x8(sh[s], hv);
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const int ky = r - 2 * d;
+          if (ky < 0 || ky > 3) continue;
+          const float w = kf[ky * 4 + c];
+          const f32x2 ww = pack2(w, w);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { ax[d][i] = fma2(ww, xv[i], ax[d][i]); ah[d][i] = fma2(ww, hv[i], ah[d][i]); }
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const int oy = oy0 + 2 * oyp + d, oxx = ox0 + ox;
+      if (oy < p.out_h && oxx < p.out_w) {
+        const int64_t o = obase + ((int64_t)oy * p.out_w + oxx) * p.minor;
+        *reinterpret_cast<uint4*>(out_x + o) = pack_bf16x8(ax[d]);
+        *reinterpret_cast<uint4*>(out_h + o) = pack_bf16x8(ah[d]);
+      }
+    }
+  } else {
+    // ---- 2 x 2 output quads from the 3 x 3 window at (qy, qx) of the staged tile; two quads per thread
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int qi = (threadIdx.x >> 2) + 64 * half;
+      const int qx = qi & 15, qy = qi >> 4;
+      f32x2 ax[2][2][4], ah[2][2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { ax[a][b][i] = pack2(0.f, 0.f); ah[a][b][i] = pack2(0.f, 0.f); }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int s = ((qy + r) * TL::ITW + qx + c) * 4 + v;
+          f32x2 xv[4], hv[4];
+          unpack_bf16x8(sx[s], xv);
+          unpack_bf16x8(sh[s], hv);
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy) {
+            const int ky = G::tap(dy, r);
+            if (ky < 0) continue;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              const int kx = G::tap(dx, c);
+              if (kx < 0) continue;
+              const float w = kf[ky * 4 + kx];
+              const f32x2 ww = pack2(w, w);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { ax[dy][dx][i] = fma2(ww, xv[i], ax[dy][dx][i]); ah[dy][dx][i] = fma2(ww, hv[i], ah[dy][dx][i]); }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int oy = oy0 + 2 * qy + dy;
+        if (oy >= p.out_h) continue;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int oxx = ox0 + 2 * qx + dx;
+          if (oxx >= p.out_w) continue;
+          const int64_t o = obase + ((int64_t)oy * p.out_w + oxx) * p.minor;
+          *reinterpret_cast<uint4*>(out_x + o) = pack_bf16x8(ax[dy][dx]);
+          *reinterpret_cast<uint4*>(out_h + o) = pack_bf16x8(ah[dy][dx]);
+        }
+      }
+    }
+  }
+}
+
+template <int UP, int DOWN>
+int launch_fir4_tile_gn(const void* in, void* out_h, void* out_x, const float* kern, const float* table, int table_ld, int act,
+                        const FirP& p, cudaStream_t st) {
+  using TL = FirTile<UP, DOWN>;
+  const int tiles_x = (p.out_w + TL::OTW - 1) / TL::OTW, tiles_y = (p.out_h + TL::OTH - 1) / TL::OTH;
+  const int cchunks = p.minor / kFirCC;
+  const int64_t blocks = p.major * tiles_y * (int64_t)tiles_x * cchunks;
+  if (blocks >= (1LL << 31)) return MUDIFF_EUNSUPPORTED;
+  static bool attr_set[16] = {};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(fir4_tile_gn_kernel<UP, DOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev] = true;
+  }
+  fir4_tile_gn_kernel<UP, DOWN><<<(unsigned)blocks, 256, TL::SMEM, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out_h,
+                                                                          (__nv_bfloat16*)out_x, kern, table, table_ld, act, p,
+                                                                          tiles_x, tiles_y, cchunks);
+  return mudiff_launch_status();
+}
+
 template <typename T>
 int launch_fir(const void* in, void* out, const float* kern, const FirP& p, cudaStream_t st) {
   constexpr int V = 16 / sizeof(T);
@@ -488,6 +704,11 @@ extern "C" int mudiff_upfirdn2d_gn(const void* x, void* out_h, void* out_x, cons
   p.out_w = (in_w * up + pad0 + pad1 - 4) / down + 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MUDIFF_BF16) {
+    static int tiled = -1;                     // MUDIFF_FIR_GN_TILED=0: the register-window kernel for every shape
+    if (tiled < 0) { const char* e = getenv("MUDIFF_FIR_GN_TILED"); tiled = (e && e[0] == '0') ? 0 : 1; }
+    if (tiled && channels % kFirCC == 0)
+      return up == 2 ? launch_fir4_tile_gn<2, 1>(x, out_h, out_x, kernel, table, table_ld, act, p, st)
+                     : launch_fir4_tile_gn<1, 2>(x, out_h, out_x, kernel, table, table_ld, act, p, st);
     return up == 2 ? launch_fir4_quad_gn<__nv_bfloat16, 2, 1>(x, out_h, out_x, kernel, table, table_ld, act, p, st)
                    : launch_fir4_quad_gn<__nv_bfloat16, 1, 2>(x, out_h, out_x, kernel, table, table_ld, act, p, st);
   }

@@ -3,6 +3,7 @@
 //   stats : per (batch, group) (sum, sumsq) in fp64, block-partial -> atomicAdd(double)
 //   apply : y = act(x * scale[b,c] + shift[b,c]),  scale = gamma*rstd, shift = beta - mean*scale
 // HBM-bound: stats reads the tensor once, apply reads once + writes once, 16-byte vectors.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -12,24 +13,26 @@ namespace {
 // Deterministic and batch-invariant: a block always owns GN_PPB consecutive pixels of one image,
 // threads reduce in a fixed order, block partials go to `partial[b][chunk][g]` and the LAST block of
 // each image (self-resetting ticket counter) adds them up in chunk order.  No floating-point atomics.
-// pixels per block: a function of (hw, C) only (=> batch-invariant): ~256 KB of bf16 per block, at least
-// 32 blocks per image for large images
+// pixels per block: a function of (hw, C) only (=> batch-invariant): ~256 KB of bf16 per block (MUDIFF_GN_CHUNK_KB; 64 KB
+// chunks cost the stand-alone statistics pass 28 -> 36 ms per bench step), at least 32 blocks per image for large images
 static inline int gn_ppb(int64_t hw, int C) {
-  int64_t a = 131072 / C; if (a < 256) a = 256;
-  int64_t b = hw / 32; if (b < 256) b = 256;
+  static int chunk_elems = 0;
+  if (!chunk_elems) { const char* e = getenv("MUDIFF_GN_CHUNK_KB"); chunk_elems = (e ? atoi(e) : 256) * 512; if (chunk_elems < 8192) chunk_elems = 8192; }
+  int64_t a = chunk_elems / C; if (a < 128) a = 128;
+  int64_t b = hw / 32; if (b < 128) b = 128;
   return (int)(a < b ? a : b);
 }
+// Statistics of one block's pixel chunk (blockIdx.x) of image blockIdx.y; returns true in the LAST block of the image, which
+// has then written the image's per-channel-group totals to `stats`.  Shared by gn_stats_kernel and gn_l2_kernel (bit-identical).
 template <typename T>
-__global__ void __launch_bounds__(256, 3) gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const T* __restrict__ x1, int c1, int ld1,
-                                int64_t hw, int groups, double* __restrict__ stats, int st_ld, int st_off,
-                                double* __restrict__ partial, unsigned int* __restrict__ tickets, int GN_PPB) {
+__device__ __forceinline__ bool gn_stats_block(const T* __restrict__ x0, int c0, int ld0, const T* __restrict__ x1, int c1, int ld1,
+                                               int64_t hw, int groups, double* stats, int st_ld, int st_off,
+                                               double* partial, unsigned int* tickets, int GN_PPB, float* s_part, bool* s_last) {
   constexpr int V = 16 / sizeof(T);
   const int C = c0 + c1;
   const int cv = C / V;
   const int b = blockIdx.y;
   const int chunks = gridDim.x;
-  extern __shared__ float s_part[];            // [lanes][C][2]
-  __shared__ bool s_last;
   // blockDim.x is a multiple of cv: each thread keeps one channel vector for the whole loop
   const int my_cv = threadIdx.x % cv;
   const int lane = threadIdx.x / cv;
@@ -84,42 +87,80 @@ __global__ void __launch_bounds__(256, 3) gn_stats_kernel(const T* __restrict__ 
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int t = atomicAdd(&tickets[b], 1u);
-    s_last = (t == (unsigned int)chunks - 1);
-    if (s_last) tickets[b] = 0;                 // self-reset for the next launch on this stream
+    *s_last = (t == (unsigned int)chunks - 1);
+    if (*s_last) tickets[b] = 0;                // self-reset for the next launch on this stream
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!*s_last) return false;
   __threadfence();
+  // totals = chunk partials added in a FIXED order (deterministic): `segs` threads per value, each adds a contiguous run of
+  // chunks (8 independent L2 loads in flight), the run sums are then added in run order.  In gn_l2_kernel every other block
+  // of the image waits for this, so it must not be a chain of `chunks` dependent L2 round trips.
   const double* pb = partial + (int64_t)b * chunks * groups * 2;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
+  const int nvals = groups * 2;
+  int segs = (int)blockDim.x / nvals;
+  if (segs < 1) segs = 1;
+  if (segs > 8) segs = 8;
+  const int cps = (chunks + segs - 1) / segs;
+  double* s_run = reinterpret_cast<double*>(s_part);      // [segs][nvals] (the float partials are dead by now)
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nvals * segs; idx += blockDim.x) {
+    const int i = idx % nvals, sg = idx / nvals;
+    const int k0 = sg * cps, k1 = (k0 + cps < chunks) ? k0 + cps : chunks;
     double a = 0.0;
-    for (int k = 0; k < chunks; ++k) a += pb[(int64_t)k * groups * 2 + i];
+    int k = k0;
+    for (; k + 8 <= k1; k += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(pb + (int64_t)(k + u) * nvals + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += v[u];
+    }
+    for (; k < k1; ++k) a += __ldcg(pb + (int64_t)k * nvals + i);
+    s_run[(size_t)sg * nvals + i] = a;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nvals; i += blockDim.x) {
+    double a = 0.0;
+    for (int sg = 0; sg < segs; ++sg) a += s_run[(size_t)sg * nvals + i];
     stats[((int64_t)b * st_ld + st_off) * 2 + i] = a;
   }
+  return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 3) gn_stats_kernel(const T* __restrict__ x0, int c0, int ld0, const T* __restrict__ x1, int c1, int ld1,
+                                int64_t hw, int groups, double* __restrict__ stats, int st_ld, int st_off,
+                                double* __restrict__ partial, unsigned int* __restrict__ tickets, int GN_PPB) {
+  extern __shared__ float s_part[];            // [lanes][C][2]
+  __shared__ bool s_last;
+  gn_stats_block<T>(x0, c0, ld0, x1, c1, ld1, hw, groups, stats, st_ld, st_off, partial, tickets, GN_PPB, s_part, &s_last);
 }
 
 // apply: each thread owns ONE channel vector (scale/shift live in registers) and walks pixels with a
 // fixed stride -> no integer division in the streaming loop, 4 independent 16-byte loads in flight.
 #define GN_APPLY_PPB 1024
+// Apply phase of one block on the pixels [p0, p1) of image blockIdx.y (shared by gn_apply_kernel and gn_l2_kernel).  The
+// statistics are read with ld.global.cg: in gn_l2_kernel another block of the SAME launch has just written them.
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const TI* __restrict__ x0, int c0, int ld0, const TI* __restrict__ x1, int c1, int ld1,
-                                const double* __restrict__ st0, int st0_ld, const double* __restrict__ st1, int st1_ld,
+__device__ __forceinline__ void gn_apply_block(const TI* __restrict__ x0, int c0, int ld0, const TI* __restrict__ x1, int c1, int ld1,
+                                const double* st0, int st0_ld, const double* st1, int st1_ld,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int64_t gb_bstride,
-                                TO* __restrict__ out, int ld_out, int64_t hw, int groups, float eps, int act) {
+                                TO* __restrict__ out, int ld_out, int64_t hw, int groups, float eps, int act,
+                                const int64_t p0, const int64_t p1, float* s_mean, float* s_rstd) {
   // vector width is chosen on the WIDER of the two element types so both sides stay <= 16 bytes
   constexpr int V = (sizeof(TI) >= sizeof(TO)) ? 16 / sizeof(TI) : 16 / sizeof(TO);
   const int C = c0 + c1;
   const int cv = C / V;
   const int b = blockIdx.y;
   const int cpg = C / groups;
-  __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
   // per-channel (sum, sumsq) of the two sources -> per-group mean / rstd (double math, once per block)
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double a = 0.0, q = 0.0;
     for (int i = 0; i < cpg; ++i) {
       const int c = g * cpg + i;
       const double* sp = c < c0 ? st0 + ((int64_t)b * st0_ld + c) * 2 : st1 + ((int64_t)b * st1_ld + (c - c0)) * 2;
-      a += sp[0]; q += sp[1];
+      a += __ldcg(sp); q += __ldcg(sp + 1);
     }
     const double cnt = (double)hw * (double)cpg;
     const double m = a / cnt;
@@ -132,6 +173,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const TI* __restrict__
   const int my_cv = threadIdx.x % cv;
   const int lane = threadIdx.x / cv;
   const int lanes = blockDim.x / cv;
+  if (lane >= lanes) return;                  // gn_l2_kernel: the block size follows x0's channel count (phase 1)
   const int ch = my_cv * V;
   float sc[V], sh[V];
 #pragma unroll
@@ -147,8 +189,6 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const TI* __restrict__
   if (ch < c0) { src = x0 + (int64_t)b * hw * ld0 + ch; ld = ld0; }
   else { src = x1 + (int64_t)b * hw * ld1 + (ch - c0); ld = ld1; }
   TO* dst = out + (int64_t)b * hw * ld_out + ch;
-  const int64_t p0 = (int64_t)blockIdx.x * GN_APPLY_PPB;
-  int64_t p1 = p0 + GN_APPLY_PPB; if (p1 > hw) p1 = hw;
   if constexpr (sizeof(TI) == sizeof(TO)) {
     // same element size on both sides: 8 raw 16-byte loads in flight per thread (latency-bound otherwise: the
     // kernel sits at ~3 blocks/SM), then convert -> scale/shift -> activation -> pack -> store one at a time
@@ -228,6 +268,70 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const TI* __restrict__
   }
 }
 
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const TI* __restrict__ x0, int c0, int ld0, const TI* __restrict__ x1, int c1, int ld1,
+                                const double* __restrict__ st0, int st0_ld, const double* __restrict__ st1, int st1_ld,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int64_t gb_bstride,
+                                TO* __restrict__ out, int ld_out, int64_t hw, int groups, float eps, int act) {
+  __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
+  const int64_t p0 = (int64_t)blockIdx.x * GN_APPLY_PPB;
+  int64_t p1 = p0 + GN_APPLY_PPB; if (p1 > hw) p1 = hw;
+  gn_apply_block<TI, TO>(x0, c0, ld0, x1, c1, ld1, st0, st0_ld, st1, st1_ld, gamma, beta, gb_bstride, out, ld_out, hw, groups, eps, act,
+                         p0, p1, s_mean, s_rstd);
+}
+
+// ---------------------------------------------------------------------------------
+// Statistics + apply in ONE launch with the second read served by L2 ("gn_l2"): block (chunk, image) computes the partial
+// statistics of its chunk exactly like gn_stats_kernel, the last block of the image publishes the totals and raises the
+// image's flag, every block of the image then normalises ITS OWN chunk - which it read a few microseconds ago, so the re-read
+// hits L2 when the chunks of all resident blocks fit there: 2 HBM passes per GroupNorm instead of 3 (see ops.GN_L2 for when
+// that pays).
+// Blocks of one image are consecutive in launch order, so they are co-resident (the host only takes this path when an image
+// has at most kGnL2MaxChunks chunks); the flag / arrival counters reset themselves (CUDA-graph replays need no host reset).
+// Results are bit-identical to gn_stats_kernel + gn_apply_kernel (same device functions, same chunking).
+// x0: statistics unknown (computed here, stored to st0); optional x1 (channel-concat partner) with known statistics st1.
+// ---------------------------------------------------------------------------------
+constexpr int kGnL2MaxChunks = 256;
+template <typename T>
+__global__ void __launch_bounds__(256, 3) gn_l2_kernel(const T* __restrict__ x0, int c0, int ld0, const T* __restrict__ x1, int c1, int ld1,
+                                double* st0, int st0_ld, const double* st1, int st1_ld, int groups0,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int64_t gb_bstride,
+                                T* __restrict__ out, int ld_out, int64_t hw, int groups, float eps, int act,
+                                double* partial, unsigned int* tickets, unsigned int* flags, unsigned int* done, int GN_PPB, unsigned int poll_ns) {
+  extern __shared__ float s_part[];            // [lanes][c0][2]
+  __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
+  __shared__ bool s_last;
+  const int b = blockIdx.y;
+  // phase 1: per-channel statistics of x0 (groups0 == c0: one "group" per channel, as mudiff_gn_stats)
+  const bool last = gn_stats_block<T>(x0, c0, ld0, nullptr, 0, 0, hw, groups0, st0, st0_ld, 0, partial, tickets, GN_PPB, s_part, &s_last);
+  if (last) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicExch(&flags[b * 32], 1u);
+  } else if (threadIdx.x == 0) {
+    // one poller per block, one 128-byte line per image, sleeping between polls: hundreds of blocks hammering one L2
+    // sector with back-to-back acquire loads starved the very atomics that release them
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + b * 32) : "memory");
+      if (!v) __nanosleep(poll_ns);
+    } while (!v);
+  }
+  __syncthreads();
+  // phase 2: normalise this block's own chunk (L2-resident)
+  const int64_t p0 = (int64_t)blockIdx.x * GN_PPB;
+  int64_t p1 = p0 + GN_PPB; if (p1 > hw) p1 = hw;
+  gn_apply_block<T, T>(x0, c0, ld0, x1, c1, ld1, st0, st0_ld, st1, st1_ld, gamma, beta, gb_bstride, out, ld_out, hw, groups, eps, act,
+                       p0, p1, s_mean, s_rstd);
+  // every block of the image has read the flag and the statistics once it arrives here: the last arrival resets them
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&done[b], 1u);
+    if (t == gridDim.x - 1) { done[b] = 0; atomicExch(&flags[b * 32], 0u); }
+  }
+}
+
 // Per-tile per-channel (sum, sumsq) float partials written by the conv epilogue -> per-channel doubles.
 // One block per image, ordered summation over the tiles (deterministic, batch-invariant).
 // rows = partial rows per image (tiles x 4 lane quadrants).  Block (b, column block of 32): thread (col, seg) adds the rows
@@ -262,6 +366,12 @@ __global__ void __launch_bounds__(1024) stats_finalize_kernel(const float* __res
   }
 }
 
+// dynamic shared memory of gn_stats_block: float partials [lanes][C][2], reused as double run sums [segs][groups * 2]
+static inline size_t gn_stats_smem(int lanes, int C, int groups, int block) {
+  int segs = block / (groups * 2); if (segs < 1) segs = 1; if (segs > 8) segs = 8;
+  const size_t a = sizeof(float) * 2 * (size_t)lanes * C, r = sizeof(double) * (size_t)segs * groups * 2;
+  return a > r ? a : r;
+}
 // scratch for block partials + ticket counters, grown on demand (single stream of use per device)
 struct StatsScratch { double* partial = nullptr; size_t cap = 0; unsigned int* tickets = nullptr; int tcap = 0; };
 static StatsScratch g_scratch[16];
@@ -307,7 +417,7 @@ int launch_stats(const void* x0, int c0, int ld0, const void* x1, int c1, int ld
   int rc = ensure_scratch(dev, (size_t)batch * chunks * groups * 2, batch, st);
   if (rc) return rc;
   dim3 grid(chunks, batch);
-  size_t smem = sizeof(float) * 2 * (size_t)lanes * C;
+  size_t smem = gn_stats_smem(lanes, C, groups, block);
   gn_stats_kernel<T><<<grid, block, smem, st>>>((const T*)x0, c0, ld0, (const T*)x1, c1, ld1, hw, groups, stats, st_ld, st_off,
                                                g_scratch[dev].partial, g_scratch[dev].tickets, GN_PPB);
   return mudiff_launch_status();
@@ -645,6 +755,46 @@ extern "C" int mudiff_gn_apply(const void* x0, int c0, int ld0, const double* st
   if (dtype_in == MUDIFF_BF16 && dtype_out == MUDIFF_F32) AP(__nv_bfloat16, float);
 #undef AP
   return MUDIFF_EUNSUPPORTED;
+}
+
+// Statistics of x0 + GroupNorm/AdaGN (+SiLU) of [x0 | x1] in ONE launch, the re-read of x0 served by L2 (gn_l2_kernel).
+// x0's per-channel (sum, sumsq) go to st0 (same values as mudiff_gn_stats); x1 (optional) comes with known statistics st1.
+// bf16 in/out.  MUDIFF_EUNSUPPORTED when the shape does not qualify (callers then run mudiff_gn_stats + mudiff_gn_apply,
+// which give bit-identical results).
+extern "C" int mudiff_gn_stats_apply(const void* x0, int c0, int ld0, double* st0, int st0_ld,
+                                     const void* x1, int c1, int ld1, const double* st1, int st1_ld, int dtype,
+                                     const float* gamma, const float* beta, int64_t gb_bstride,
+                                     void* out, int ld_out, int batch, int64_t hw, int groups, float eps, int act, void* stream) {
+  if (batch <= 0 || hw <= 0 || groups <= 0 || c0 <= 0 || c1 < 0 || !x0 || !st0 || !out || st0_ld < c0) return MUDIFF_EINVAL;
+  if (act != MUDIFF_ACT_NONE && act != MUDIFF_ACT_SILU) return MUDIFF_EINVAL;
+  if (!x1) c1 = 0;
+  if (c1 > 0 && !st1) return MUDIFF_EINVAL;
+  if (dtype != MUDIFF_BF16 || batch > 65535) return MUDIFF_EUNSUPPORTED;
+  constexpr int V = 8;
+  const int C = c0 + c1;
+  if (C % V || c0 % V || ld0 % V || (x1 && ld1 % V) || ld_out % V || C > GN_MAX_C || C % groups || groups > GN_MAX_C / 4)
+    return MUDIFF_EUNSUPPORTED;
+  if (((uintptr_t)x0 % 16) || (x1 && ((uintptr_t)x1 % 16)) || ((uintptr_t)out % 16)) return MUDIFF_EUNSUPPORTED;
+  const int cv0 = c0 / V, cv = C / V;
+  const int block = (256 / cv0) * cv0;            // phase 1 geometry == launch_stats(x0 alone): bit-identical statistics
+  if (block < cv0 || block / cv < 1 || (block / cv) * cv * 2 < block) return MUDIFF_EUNSUPPORTED;
+  const int lanes = block / cv0;
+  const int ppb = gn_ppb(hw, c0);
+  const int chunks = (int)((hw + ppb - 1) / ppb);
+  if (chunks > kGnL2MaxChunks) return MUDIFF_EUNSUPPORTED;   // all blocks of an image must be co-resident (they wait for each other)
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
+  int rc = ensure_scratch(dev, (size_t)batch * chunks * c0 * 2, 34 * batch, st);
+  if (rc) return rc;
+  unsigned int* ctr = g_scratch[dev].tickets;
+  static int poll_ns = -1;
+  if (poll_ns < 0) { const char* e = getenv("MUDIFF_GN_POLL_NS"); poll_ns = e ? atoi(e) : 1000; }
+  const size_t smem = gn_stats_smem(lanes, c0, c0, block);
+  gn_l2_kernel<__nv_bfloat16><<<dim3(chunks, batch), block, smem, st>>>(
+      (const __nv_bfloat16*)x0, c0, ld0, (const __nv_bfloat16*)x1, c1, ld1, st0, st0_ld, st1, st1_ld, c0, gamma, beta, gb_bstride,
+      (__nv_bfloat16*)out, ld_out, hw, groups, eps, act, g_scratch[dev].partial, ctr, ctr + 2 * batch, ctr + batch, ppb, (unsigned int)poll_ns);
+  return mudiff_launch_status();
 }
 
 extern "C" int mudiff_gn_scale_shift(const double* st0, int st0_ld, int c0, const double* st1, int st1_ld, int c1,

@@ -17,6 +17,7 @@ import os as _os
 _ENV_FLAGS = 2 if _os.environ.get('MUDIFF_HALO', '1') == '0' else 0     # debug knob: forbid halo staging
 _ENV_FLAGS |= int(_os.environ.get('MUDIFF_XF_DBG', '0')) << 20        # timing ablations of the operand transform
 _ENV_FLAGS |= 1024 if _os.environ.get('MUDIFF_BCAP12', '0') == '1' else 0   # ablation: the older, larger B ring (12 sub-tiles)
+_ENV_FLAGS |= 0x400000 if _os.environ.get('MUDIFF_NT128', '1') == '0' else 0   # ablation: N = 384 as two 192-column tiles (one accumulator stage) instead of three of 128
 
 # Fused epilogue statistics (conv_tc butterfly reduction) are implemented and tested, but since the MMA issue
 # loop got fast they cost more than the stand-alone HBM-bound statistics pass for every N <= 256 (measured,
@@ -293,11 +294,54 @@ def gn_single_pass(x, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act
     return out
 
 
+# Statistics + apply in one launch, the second read of the tensor served by L2 (mudiff_gn_stats_apply); bit-identical to
+# gn_stats + gn_apply, so the choice may depend on the batch.  Measured on B200 (profiles/r02_gn_l2.md): at B = 64 the blocks of
+# an image wait for each other through a chain of dependent global round trips (partials -> ticket -> totals -> flag) that
+# three resident blocks per SM do not cover - 58 ms (256 KB chunks, no L2 reuse) to 106 ms (64 KB chunks) against 43 + 17 ms
+# for the two launches - so `auto` (default) takes it only where the tensor fits L2 anyway (B <= 4 at 256^2: one launch less
+# per GroupNorm, +0.7 %); 1 = always, 0 = never.
+_gl2 = _os.environ.get('MUDIFF_GN_L2', 'auto')
+GN_L2 = -1 if _gl2 == 'auto' else int(_gl2)
+GN_L2_MAX_BYTES = 48 << 20
+
+
+def gn_stats_apply(srcs, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_NONE):
+    """act(GN([x0 | x1]) * gamma + beta) where x0's statistics are not known yet (computed here and attached to x0) and the
+    optional x1 already carries its own.  Returns None when the kernel does not take the shape."""
+    x0 = srcs[0]
+    x1 = srcs[1] if len(srcs) > 1 else None
+    if not GN_L2 or x0.dtype != torch.bfloat16 or (x1 is not None and x1.dtype != torch.bfloat16):
+        return None
+    b, c0, h, w = x0.shape
+    if GN_L2 < 0 and x0.numel() * 2 > GN_L2_MAX_BYTES:
+        return None
+    c1 = x1.shape[1] if x1 is not None else 0
+    s1 = getattr(x1, _CHSTATS) if x1 is not None else None
+    cs = torch.empty((b, c0, 2), dtype=torch.float64, device=x0.device)
+    out = empty_nhwc(b, c0 + c1, h, w, x0.dtype, x0.device)
+    rc = L.lib().mudiff_gn_stats_apply(x0.data_ptr(), c0, _pix_ld(x0), cs.data_ptr(), c0,
+                                       x1.data_ptr() if x1 is not None else None, c1, _pix_ld(x1) if x1 is not None else 0,
+                                       s1.data_ptr() if s1 is not None else None, s1.stride(0) // 2 if s1 is not None else 0,
+                                       L.dtype_code(x0.dtype),
+                                       gamma.data_ptr() if gamma is not None else None,
+                                       beta.data_ptr() if beta is not None else None, gb_bstride,
+                                       out.data_ptr(), c0 + c1, b, h * w, groups, float(eps), act, L.stream_ptr(x0.device))
+    if rc == L.EUNSUPPORTED:
+        return None
+    L.check(rc, 'gn_stats_apply')
+    set_chstats(x0, cs)
+    return out
+
+
 def gn_apply_auto(srcs, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_NONE):
-    """GroupNorm (+AdaGN, +act) of one tensor or the channel-concat of two: single-pass kernel when the statistics
-    of a lone source are not known yet, else statistics (cached per tensor) + apply."""
-    if len(srcs) == 1 and getattr(srcs[0], _CHSTATS, None) is None:
-        y = gn_single_pass(srcs[0], groups, gamma, beta, gb_bstride, eps, act)
+    """GroupNorm (+AdaGN, +act) of one tensor or the channel-concat of two: one launch (statistics + apply, gn_stats_apply)
+    when the statistics of the first source are not known yet, else statistics (cached per tensor) + apply."""
+    if getattr(srcs[0], _CHSTATS, None) is None and (len(srcs) == 1 or getattr(srcs[1], _CHSTATS, None) is not None):
+        if len(srcs) == 1:
+            y = gn_single_pass(srcs[0], groups, gamma, beta, gb_bstride, eps, act)
+            if y is not None:
+                return y
+        y = gn_stats_apply(srcs, groups, gamma, beta, gb_bstride, eps, act)
         if y is not None:
             return y
     return gn_apply(srcs, [get_chstats(t) for t in srcs], groups, gamma=gamma, beta=beta, gb_bstride=gb_bstride, eps=eps, act=act)
@@ -530,7 +574,7 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
                 cs = buf[:, off:off + n]
             L.check(L.lib().mudiff_stats_finalize(partial.data_ptr(), tpi * 4, n, buf.data_ptr(), buf.shape[1], off, b, st),
                     'stats_finalize')
-        elif stats_out is not None or not (GN_SINGLE_PASS and region is out):
+        elif stats_out is not None or not ((GN_SINGLE_PASS or GN_L2) and region is out):
             cs = gn_stats(region, out=stats_out)
         else:
             cs = None                    # lazy: the consuming GroupNorm computes them (single-pass kernel or get_chstats)

@@ -139,6 +139,42 @@ def test_groupnorm_adagn_silu(M, dtype, c0, c1):
     np.testing.assert_allclose(y.float().cpu().numpy(), ref.numpy(), rtol=0, atol=tol)
 
 
+@pytest.mark.parametrize('shape', [(5, 64, 0, 64, 64), (3, 384, 0, 32, 32), (4, 64, 0, 256, 256), (2, 256, 128, 64, 64), (70, 128, 128, 16, 16),
+                                   (3, 128, 64, 40, 24), (2, 64, 256, 32, 32), (1, 64, 0, 30, 30), (2, 512, 0, 64, 64)])
+@pytest.mark.parametrize('adagn', [False, True])
+def test_groupnorm_stats_apply_one_launch(M, shape, adagn):
+    """mudiff_gn_stats_apply (statistics of x0 + GroupNorm/AdaGN + SiLU of [x0 | x1] in one launch, second read from L2) is
+    BIT-IDENTICAL to mudiff_gn_stats + mudiff_gn_apply - output and exported statistics - for one and two sources, ragged
+    sizes, more images than resident blocks; repeated launches (self-resetting flags / counters) stay identical."""
+    from mudiff_b200 import ops
+    torch.manual_seed(12)
+    b, c0, c1, h, w = shape
+    c = c0 + c1
+    groups = min(c // 4, 32)
+    x0 = ops.as_nhwc((torch.randn(b, c0, h, w, device='cuda') * 1.5 + 0.4).to(torch.bfloat16))
+    x1 = ops.as_nhwc((torch.randn(b, c1, h, w, device='cuda') - 0.3).to(torch.bfloat16)) if c1 else None
+    gb = torch.cat([1 + 0.2 * torch.randn(b, c), 0.3 * torch.randn(b, c)], dim=1).cuda() if adagn else None
+    kw = dict(gamma=gb, beta=gb[:, c:], gb_bstride=2 * c) if adagn else {}
+    srcs = [x0] + ([x1] if c1 else [])
+    st = [ops.gn_stats(t) for t in srcs]
+    ref = ops.gn_apply(srcs, st, groups, act=1, **kw)
+    xc = torch.cat([t.float() for t in srcs], 1)
+    tref = F.group_norm(xc, groups, eps=1e-6)
+    if adagn:
+        tref = tref * gb[:, :c, None, None] + gb[:, c:, None, None]
+    assert (ref.float() - F.silu(tref)).abs().max().item() <= 6e-2
+    ops.GN_L2 = True
+    for _ in range(3):
+        y0 = x0.clone()
+        s2 = [y0] + ([x1.clone()] if c1 else [])
+        if c1:
+            ops.set_chstats(s2[1], st[1])
+        y = ops.gn_stats_apply(s2, groups, act=1, **kw)
+        assert y is not None, "shape should qualify for the one-launch kernel"
+        assert torch.equal(y, ref)
+        assert torch.equal(ops.get_chstats(y0), st[0])
+
+
 @pytest.mark.parametrize('shape', [(5, 64, 64, 64), (3, 384, 32, 32), (4, 64, 256, 256), (2, 256, 128, 128), (70, 128, 16, 16)])
 @pytest.mark.parametrize('adagn', [False, True])
 def test_groupnorm_single_pass(M, shape, adagn):
