@@ -46,6 +46,7 @@ struct TcParams {
   int a_batched, w_batched;
   uint32_t a_slot_bytes, b_sub_bytes, off_b, off_stats, off_bar;
   int a_slots, a_ring, b_slots, stationary, b_total_subs;   // a_slots = MT * a_ring
+  int issuers;                                // conv_tc2_kernel: issuing warps in the leader CTA (1 or 2), a_slots = issuers * a_ring
   uint32_t idesc;
   int acc_stride, acc_stages, tmem_cols;
   int base_off_variant;

@@ -118,18 +118,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   if (warp == 0) {
     // =========================== A producer (each CTA, its own tile) ===========================
     if (lane == 0 && !p.dbg_dry) {
-      uint32_t cnt = 0;
-      const uint32_t ns = (uint32_t)p.a_slots;
+      // one A ring per issuing warp (units alternate between the issuers): every ring keeps exactly one in-order consumer
+      uint32_t cnt0 = 0u, cnt1 = 0u;
+      const uint32_t nis = (uint32_t)p.issuers, ar = (uint32_t)p.a_ring;
       for (long long u = u_begin; u < u_end; ++u) {
         const int b = (int)(u / p.gpi);
         const int r = (int)(u - (long long)b * p.gpi) * 2 + (int)rank;
         const int ty = r / p.tiles_x;
         const int y0 = ty * p.tile_h, x0 = (r - ty * p.tiles_x) * p.tile_w;
+        const uint32_t ring = nis == 2 ? (uint32_t)((u - u_begin) & 1) : 0u;
         for_each_group(p, [&](int s, int cb, int tap, int nb) {
           const CUtensorMap* mapA = s == 0 ? &mapA0 : (s == 1 ? &mapA1 : &mapA2);
-          const uint32_t slot = cnt % ns;
-          const uint32_t par = ((cnt / ns) & 1u) ^ 1u;
-          mbar_wait(&a_empty[slot], par, bar_block, (int)cnt);
+          const uint32_t c = ring ? cnt1 : cnt0;
+          const uint32_t slot = ring * ar + c % ar;
+          const uint32_t par = ((c / ar) & 1u) ^ 1u;
+          mbar_wait(&a_empty[slot], par, bar_block, (int)c);
           uint8_t* sa = smem + (size_t)slot * p.a_slot_bytes;
           const uint32_t bytes = nb == 9 ? (uint32_t)(p.tile_w + 2) * (p.tile_h + 2) * 128u : 128u * 128u;
           if (rank == 0) mbar_expect_tx(&a_full[slot], 2u * bytes);           // both CTAs' tiles complete on the leader's barrier
@@ -141,7 +144,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             const int dx = p.seg_taps[s] == 9 ? tap % 3 - 1 : 0;
             tma2_load_4d(sa, mapA, bar, cb * 64, x0 + dx, y0 + dy, b);
           }
-          ++cnt;
+          if (ring) cnt1 = c + 1; else cnt0 = c + 1;
         });
       }
     }
@@ -153,12 +156,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       for (int i = 0; i < p.b_total_subs; ++i)
         tma2_load_3d(smem + p.off_b + (size_t)i * p.b_sub_bytes, &mapW, bar, i * 64, (int)rank * (p.n_tile / 2), 0);
     }
-  } else if (warp == 2) {
-    // =========================== MMA issuer (leader CTA only) =============================
+  } else if (warp == 2 || (warp == 3 && p.issuers == 2)) {
+    // =========================== MMA issuers (leader CTA only) =============================
+    // One thread cannot issue a UMMA faster than every ~54 clocks (profiles/r02_umma_collector_probe.md), above the 40-clock
+    // operand-read time of a 256 x 64 x 16 pair UMMA.  Optional second issuer (p.issuers == 2, opt-in): warp 2 takes the even
+    // units of the cluster's range (accumulator stages 0, 2), warp 3 the odd ones (stages 1, 3), each from its own A ring.
     if (rank == 0) {
+      const int me = warp - 2;
+      const int nis = p.issuers;
       const bool leader = elect_one();
+      const uint32_t ar = (uint32_t)p.a_ring;
       uint32_t a_slot = 0, a_phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t hi_b = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t hi_a_halo = ((10u * 128u) >> 4) | (1u << 14) | (2u << 29);
@@ -169,14 +177,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const bool dry = p.dbg_dry != 0;                      // timing ablation: no operand traffic
       if (!dry) mbar_wait(w_full, 0, bar_block, -1);
       tc_fence_after();
-      for (long long u = u_begin; u < u_end; ++u) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, bar_block, (int)(u - u_begin));
+      for (long long u = u_begin + me; u < u_end; u += nis) {
+        const long long iu = u - u_begin;
+        const int acc = (int)(iu % p.acc_stages);
+        const uint32_t acc_phase = (uint32_t)((iu / p.acc_stages) & 1);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, bar_block, (int)iu);
         tc_fence_after();
         uint32_t accum = 0;
         const uint32_t d_mine = tmem_base + (uint32_t)(acc * p.acc_stride);
         for_each_group(p, [&](int s, int cb, int tap, int nb) {
-          const uint32_t sl = a_slot, ph = a_phase;
-          if (!dry) mbar_wait(&a_full[sl], ph, bar_block, (int)(u - u_begin));
+          const uint32_t sl = (uint32_t)me * ar + a_slot, ph = a_phase;
+          if (!dry) mbar_wait(&a_full[sl], ph, bar_block, (int)iu);
           tc_fence_after();
           const uint32_t alo = a_lo_base + sl * a_step;
           const uint32_t hi_a = nb == 9 ? hi_a_halo : hi_b;
@@ -199,10 +210,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             }
           }
           if (leader && !dry) tc2_commit_mc(&a_empty[sl]);    // frees the slot in BOTH CTAs
-          if (++a_slot == (uint32_t)p.a_slots) { a_slot = 0; a_phase ^= 1u; }
+          if (++a_slot == ar) { a_slot = 0; a_phase ^= 1u; }
         });
         if (leader) tc2_commit_mc(&tfull_bar[acc]);           // both CTAs' epilogues
-        if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
         __syncwarp();
       }
     }
@@ -287,7 +297,14 @@ static bool plan_pair(const mudiff_conv_desc* d, const TcParams& p1, int ktot, T
   if (b_total + (uint32_t)min_slots * p.a_slot_bytes + fixed > kSmemMax) return false;
   int as = (int)((kSmemMax - fixed - b_total) / p.a_slot_bytes);
   p.a_slots = as > 8 ? 8 : as;
-  p.a_ring = p.a_slots;
+  // MUDIFF_PAIR_ISSUERS=2: two issuing warps for N = 64.  Lifts the issue floor (no operands, no epilogue: 1280 -> 1548 TFLOP/s
+  // at K = 576) but not the full kernel (964 -> 959, bound by epilogue + operand traffic), and halves the A ring per issuer,
+  // which costs the three-segment fused-shortcut launches 20 % (780 -> 629): off by default (profiles/r02_pair_issuers.md).
+  static int two_issuers = -1;
+  if (two_issuers < 0) { const char* e = getenv("MUDIFF_PAIR_ISSUERS"); two_issuers = (e && e[0] == '2') ? 1 : 0; }
+  p.issuers = (two_issuers && p.n_tile == 64 && p.a_slots >= 4 && p.total_units >= MUDIFF_NUM_SMS) ? 2 : 1;
+  if (p.issuers == 2) p.a_slots &= ~1;
+  p.a_ring = p.a_slots / p.issuers;
   p.off_b = (uint32_t)p.a_slots * p.a_slot_bytes;
   p.off_stats = p.off_b + b_total;
   p.off_bar = p.off_stats + ((stats_bytes + 1023u) & ~1023u);
