@@ -140,6 +140,11 @@ int mudiff_gn_fused(const void* x, void* out, int c, int batch, int64_t hw, int 
 int mudiff_gn_scale_shift(const double* st0, int st0_ld, int c0, const double* st1, int st1_ld, int c1,
                           const float* gamma, const float* beta, int64_t gb_bstride, int batch, int64_t hw,
                           int groups, float eps, float* table, void* stream);
+/* mudiff_gn_stats(x0 -> st0) followed by mudiff_gn_scale_shift([st0 | st1] -> table) as ONE launch (the block that completes an
+ * image's statistics writes its table rows); identical values, one launch less per GroupNorm that a consumer applies itself. */
+int mudiff_gn_stats_table(const void* x0, int c0, int ld0, int dtype, double* st0, int st0_ld,
+                          int c1, const double* st1, int st1_ld, const float* gamma, const float* beta,
+                          int64_t gb_bstride, int batch, int64_t hw, int groups, float eps, float* table, void* stream);
 
 /* partial float[batch*rows_per_image][n][2] (written by mudiff_conv_tc: one row per pixel tile and TMEM lane quadrant,
  * rows_per_image = 4 * tiles per image) -> chstats[b][st_off + c][2]; fixed summation order (deterministic) */

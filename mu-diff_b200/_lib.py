@@ -52,6 +52,7 @@ PROTOTYPES = {
     'mudiff_posterior_update': [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _P, _I, _L, _P],
     'mudiff_gn_stats': [_P, _I, _I, _I, _I, _L, _P, _I, _I, _P],
     'mudiff_gn_fused': [_P, _P, _I, _I, _L, _I, _P, _P, _L, _F, _I, _P, _I, _I, _P],
+    'mudiff_gn_stats_table': [_P, _I, _I, _I, _P, _I, _I, _P, _I, _P, _P, _L, _I, _L, _I, _F, _P, _P],
     'mudiff_gn_scale_shift': [_P, _I, _I, _P, _I, _I, _P, _P, _L, _I, _L, _I, _F, _P, _P],
     'mudiff_stats_finalize': [_P, _I, _I, _P, _I, _I, _I, _P],
     'mudiff_gn_stats_apply': [_P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P, _I, _I, _L, _I, _F, _I, _P],

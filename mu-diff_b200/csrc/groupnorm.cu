@@ -654,17 +654,18 @@ __global__ void __launch_bounds__(256, 1) gn_fused_kernel(const GnFusedP p) {
 // Folded GroupNorm / AdaGN parameters for consumers that apply the normalisation themselves (mudiff_conv_tc's
 // A-operand transform): table[b][c] = (scale, shift) with scale = gamma * rstd, shift = beta - mean * scale.
 // One block per image, one thread per channel; same double-precision group statistics as gn_apply_kernel.
-__global__ void gn_scale_shift_kernel(const double* __restrict__ st0, int st0_ld, int c0, const double* __restrict__ st1,
-                                      int st1_ld, int c1, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      int64_t gb_bstride, double hw, int groups, float eps, float* __restrict__ table) {
-  __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
-  const int C = c0 + c1, b = blockIdx.x, cpg = C / groups;
+// table[b][c] = (scale, shift) of image b (all threads of the block; shared by gn_scale_shift_kernel and gn_stats_table_kernel)
+__device__ __forceinline__ void gn_table_block(const double* st0, int st0_ld, int c0, const double* st1, int st1_ld, int c1,
+                                               const float* __restrict__ gamma, const float* __restrict__ beta, int64_t gb_bstride,
+                                               double hw, int groups, float eps, float* __restrict__ table, int b,
+                                               float* s_mean, float* s_rstd) {
+  const int C = c0 + c1, cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double a = 0.0, q = 0.0;
     for (int i = 0; i < cpg; ++i) {
       const int c = g * cpg + i;
       const double* sp = c < c0 ? st0 + ((int64_t)b * st0_ld + c) * 2 : st1 + ((int64_t)b * st1_ld + (c - c0)) * 2;
-      a += sp[0]; q += sp[1];
+      a += __ldcg(sp); q += __ldcg(sp + 1);
     }
     const double cnt = hw * (double)cpg;
     const double m = a / cnt;
@@ -682,6 +683,30 @@ __global__ void gn_scale_shift_kernel(const double* __restrict__ st0, int st0_ld
     table[((int64_t)b * C + c) * 2 + 0] = sc;
     table[((int64_t)b * C + c) * 2 + 1] = be - s_mean[g] * sc;
   }
+}
+
+__global__ void gn_scale_shift_kernel(const double* __restrict__ st0, int st0_ld, int c0, const double* __restrict__ st1,
+                                      int st1_ld, int c1, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      int64_t gb_bstride, double hw, int groups, float eps, float* __restrict__ table) {
+  __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
+  gn_table_block(st0, st0_ld, c0, st1, st1_ld, c1, gamma, beta, gb_bstride, hw, groups, eps, table, blockIdx.x, s_mean, s_rstd);
+}
+
+// Statistics of x0 AND the folded (scale, shift) table of GroupNorm/AdaGN over [x0 | x1] in one launch: the last block of an
+// image (the one that adds up the chunk partials) goes on to write the image's table rows.  Same values as mudiff_gn_stats +
+// mudiff_gn_scale_shift; one launch less per fused GroupNorm (the sampling loop at batch 1 is launch-latency bound).
+template <typename T>
+__global__ void __launch_bounds__(256, 3) gn_stats_table_kernel(const T* __restrict__ x0, int c0, int ld0, double* st0, int st0_ld,
+                                int c1, const double* st1, int st1_ld, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                int64_t gb_bstride, int64_t hw, int groups, float eps, float* __restrict__ table,
+                                double* partial, unsigned int* tickets, int GN_PPB) {
+  extern __shared__ float s_part[];
+  __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
+  __shared__ bool s_last;
+  if (!gn_stats_block<T>(x0, c0, ld0, nullptr, 0, 0, hw, c0, st0, st0_ld, 0, partial, tickets, GN_PPB, s_part, &s_last)) return;
+  __threadfence();
+  __syncthreads();                               // the totals written by this block's threads are visible to all of them
+  gn_table_block(st0, st0_ld, c0, st1, st1_ld, c1, gamma, beta, gb_bstride, (double)hw, groups, eps, table, blockIdx.y, s_mean, s_rstd);
 }
 
 __global__ void gap_mean_kernel(const double* __restrict__ stats, float* __restrict__ out, int n, double inv) {
@@ -755,6 +780,40 @@ extern "C" int mudiff_gn_apply(const void* x0, int c0, int ld0, const double* st
   if (dtype_in == MUDIFF_BF16 && dtype_out == MUDIFF_F32) AP(__nv_bfloat16, float);
 #undef AP
   return MUDIFF_EUNSUPPORTED;
+}
+
+// mudiff_gn_stats(x0 -> st0) + mudiff_gn_scale_shift([st0 | st1] -> table) in one launch (gn_stats_table_kernel); identical values.
+extern "C" int mudiff_gn_stats_table(const void* x0, int c0, int ld0, int dtype, double* st0, int st0_ld,
+                                     int c1, const double* st1, int st1_ld, const float* gamma, const float* beta,
+                                     int64_t gb_bstride, int batch, int64_t hw, int groups, float eps, float* table, void* stream) {
+  if (!x0 || !st0 || !table || batch <= 0 || hw <= 0 || groups <= 0 || c0 <= 0 || c1 < 0 || st0_ld < c0) return MUDIFF_EINVAL;
+  if (!st1) c1 = 0;
+  const int C = c0 + c1;
+  if (C > GN_MAX_C || C % groups || groups > GN_MAX_C / 4 || batch > 65535) return MUDIFF_EUNSUPPORTED;
+  if (dtype != MUDIFF_BF16 && dtype != MUDIFF_F32) return MUDIFF_EUNSUPPORTED;
+  const int V = dtype == MUDIFF_BF16 ? 8 : 4;
+  if (c0 % V || ld0 % V || ((uintptr_t)x0 % 16)) return MUDIFF_EUNSUPPORTED;
+  const int cv = c0 / V;
+  int block = (256 / cv) * cv;
+  if (block < cv) block = cv;
+  const int lanes = block / cv;
+  const int ppb = gn_ppb(hw, c0);
+  const int chunks = (int)((hw + ppb - 1) / ppb);
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
+  int rc = ensure_scratch(dev, (size_t)batch * chunks * c0 * 2, batch, st);
+  if (rc) return rc;
+  const size_t smem = gn_stats_smem(lanes, c0, c0, block);
+  if (dtype == MUDIFF_BF16)
+    gn_stats_table_kernel<__nv_bfloat16><<<dim3(chunks, batch), block, smem, st>>>(
+        (const __nv_bfloat16*)x0, c0, ld0, st0, st0_ld, c1, st1, st1_ld, gamma, beta, gb_bstride, hw, groups, eps, table,
+        g_scratch[dev].partial, g_scratch[dev].tickets, ppb);
+  else
+    gn_stats_table_kernel<float><<<dim3(chunks, batch), block, smem, st>>>(
+        (const float*)x0, c0, ld0, st0, st0_ld, c1, st1, st1_ld, gamma, beta, gb_bstride, hw, groups, eps, table,
+        g_scratch[dev].partial, g_scratch[dev].tickets, ppb);
+  return mudiff_launch_status();
 }
 
 // Statistics of x0 + GroupNorm/AdaGN (+SiLU) of [x0 | x1] in ONE launch, the re-read of x0 served by L2 (gn_l2_kernel).

@@ -63,7 +63,7 @@ class AdaptiveGroupNorm(nn.Module):
         L.require_cuda(*srcs)
         gb = self.style_params(style) if gb is None else gb
         c = self.in_channel
-        return ops.gn_scale_shift(srcs, [ops.get_chstats(t) for t in srcs], self.num_groups, gamma=gb, beta=gb[:, c:],
+        return ops.gn_scale_shift(srcs, None, self.num_groups, gamma=gb, beta=gb[:, c:],
                                   gb_bstride=gb.stride(0), eps=self.norm.eps)
 
     def forward(self, input, style, act=L.ACT_NONE, gb=None):

@@ -244,6 +244,9 @@ def xform_profitable(seg_channels, extra_segments=0, pixels=None) -> bool:
     return FUSED_GN == 1 and len(seg_channels) == 1 and seg_channels[0] == 64 and extra_segments == 0
 
 
+FUSED_STATS_TABLE = _os.environ.get('MUDIFF_FUSED_STATS_TABLE', '1') != '0'
+
+
 def gn_scale_shift(srcs, chstats, groups, gamma=None, beta=None, gb_bstride=0, eps=1e-6):
     """Folded GroupNorm / AdaGN parameters of the channel-concat of `srcs`: float [B, C, 2] = (scale, shift) with
     GN(x)*gamma + beta == x*scale + shift.  Consumed by conv(..., segs=[(x, taps, (table, c_off))]) which applies
@@ -251,9 +254,26 @@ def gn_scale_shift(srcs, chstats, groups, gamma=None, beta=None, gb_bstride=0, e
     x0 = srcs[0]
     b, c0, h, w = x0.shape
     c1 = srcs[1].shape[1] if len(srcs) > 1 else 0
+    table = torch.empty((b, c0 + c1, 2), dtype=torch.float32, device=x0.device)
+    if chstats is None:
+        # lazily computed statistics: x0's are not known yet -> statistics + table in ONE launch (mudiff_gn_stats_table)
+        s1 = getattr(srcs[1], _CHSTATS, None) if len(srcs) > 1 else None
+        if FUSED_STATS_TABLE and getattr(x0, _CHSTATS, None) is None and (len(srcs) == 1 or s1 is not None) \
+                and x0.dtype in (torch.bfloat16, torch.float32) and is_nhwc_view(x0):
+            cs = torch.empty((b, c0, 2), dtype=torch.float64, device=x0.device)
+            rc = L.lib().mudiff_gn_stats_table(x0.data_ptr(), c0, _pix_ld(x0), L.dtype_code(x0.dtype), cs.data_ptr(), c0,
+                                               c1, s1.data_ptr() if s1 is not None else None,
+                                               s1.stride(0) // 2 if s1 is not None else 0,
+                                               gamma.data_ptr() if gamma is not None else None,
+                                               beta.data_ptr() if beta is not None else None, gb_bstride,
+                                               b, h * w, groups, float(eps), table.data_ptr(), L.stream_ptr(x0.device))
+            if rc != L.EUNSUPPORTED:
+                L.check(rc, 'gn_stats_table')
+                set_chstats(x0, cs)
+                return table
+        chstats = [get_chstats(t) for t in srcs]
     s0 = chstats[0]
     s1 = chstats[1] if len(srcs) > 1 else None
-    table = torch.empty((b, c0 + c1, 2), dtype=torch.float32, device=x0.device)
     rc = L.lib().mudiff_gn_scale_shift(s0.data_ptr(), s0.stride(0) // 2, c0,
                                        s1.data_ptr() if s1 is not None else None,
                                        s1.stride(0) // 2 if s1 is not None else 0, c1,
@@ -574,7 +594,7 @@ def conv(segs, wt, n, *, bias=None, rowbias=None, residual=None, alpha=1.0, beta
                 cs = buf[:, off:off + n]
             L.check(L.lib().mudiff_stats_finalize(partial.data_ptr(), tpi * 4, n, buf.data_ptr(), buf.shape[1], off, b, st),
                     'stats_finalize')
-        elif stats_out is not None or not ((GN_SINGLE_PASS or GN_L2) and region is out):
+        elif stats_out is not None or not ((GN_SINGLE_PASS or GN_L2 or FUSED_STATS_TABLE) and region is out):
             cs = gn_stats(region, out=stats_out)
         else:
             cs = None                    # lazy: the consuming GroupNorm computes them (single-pass kernel or get_chstats)

@@ -139,6 +139,36 @@ def test_groupnorm_adagn_silu(M, dtype, c0, c1):
     np.testing.assert_allclose(y.float().cpu().numpy(), ref.numpy(), rtol=0, atol=tol)
 
 
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('shape', [(3, 64, 0, 64, 64), (2, 128, 128, 32, 32), (1, 64, 256, 30, 22), (5, 512, 0, 16, 16)])
+def test_groupnorm_stats_and_table_one_launch(M, shape, dtype):
+    """mudiff_gn_stats_table (statistics of x0 + folded AdaGN (scale, shift) table of [x0 | x1] in one launch) returns exactly
+    the table and statistics of mudiff_gn_stats + mudiff_gn_scale_shift."""
+    from mudiff_b200 import ops
+    torch.manual_seed(13)
+    b, c0, c1, h, w = shape
+    c = c0 + c1
+    groups = min(c // 4, 32)
+    x0 = ops.as_nhwc((torch.randn(b, c0, h, w, device='cuda') * 1.5 + 0.4).to(dtype))
+    x1 = ops.as_nhwc((torch.randn(b, c1, h, w, device='cuda') - 0.3).to(dtype)) if c1 else None
+    gb = torch.cat([1 + 0.2 * torch.randn(b, c), 0.3 * torch.randn(b, c)], dim=1).cuda()
+    kw = dict(gamma=gb, beta=gb[:, c:], gb_bstride=2 * c)
+    srcs = [x0] + ([x1] if c1 else [])
+    st = [ops.gn_stats(t) for t in srcs]
+    ref = ops.gn_scale_shift(srcs, st, groups, **kw)
+    ops.FUSED_STATS_TABLE = True
+    for _ in range(2):
+        y0 = x0.clone()
+        s2 = [y0] + ([x1.clone()] if c1 else [])
+        if c1:
+            ops.set_chstats(s2[1], st[1])
+        launches = ops.L.lib().mudiff_launch_count()
+        tab = ops.gn_scale_shift(s2, None, groups, **kw)
+        assert ops.L.lib().mudiff_launch_count() - launches == 1
+        assert torch.equal(tab, ref)
+        assert torch.equal(ops.get_chstats(y0), st[0])
+
+
 @pytest.mark.parametrize('shape', [(5, 64, 0, 64, 64), (3, 384, 0, 32, 32), (4, 64, 0, 256, 256), (2, 256, 128, 64, 64), (70, 128, 128, 16, 16),
                                    (3, 128, 64, 40, 24), (2, 64, 256, 32, 32), (1, 64, 0, 30, 30), (2, 512, 0, 64, 64)])
 @pytest.mark.parametrize('adagn', [False, True])
