@@ -147,12 +147,11 @@ __device__ __forceinline__ void gn_apply_block(const TI* __restrict__ x0, int c0
                                 const double* st0, int st0_ld, const double* st1, int st1_ld,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int64_t gb_bstride,
                                 TO* __restrict__ out, int ld_out, int64_t hw, int groups, float eps, int act,
-                                const int64_t p0, const int64_t p1, float* s_mean, float* s_rstd) {
+                                const int64_t p0, const int64_t p1, float* s_mean, float* s_rstd, const int b) {
   // vector width is chosen on the WIDER of the two element types so both sides stay <= 16 bytes
   constexpr int V = (sizeof(TI) >= sizeof(TO)) ? 16 / sizeof(TI) : 16 / sizeof(TO);
   const int C = c0 + c1;
   const int cv = C / V;
-  const int b = blockIdx.y;
   const int cpg = C / groups;
   // per-channel (sum, sumsq) of the two sources -> per-group mean / rstd (double math, once per block)
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
@@ -274,10 +273,13 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const TI* __restrict__
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int64_t gb_bstride,
                                 TO* __restrict__ out, int ld_out, int64_t hw, int groups, float eps, int act) {
   __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
+  // (walking the batch backwards, so that the first reads hit what the statistics pass left in L2, was measured: 43.6 -> 43.2 ms
+  // per step at B = 64 - the tensors are 4 - 8x the L2; not kept)
+  const int b = blockIdx.y;
   const int64_t p0 = (int64_t)blockIdx.x * GN_APPLY_PPB;
   int64_t p1 = p0 + GN_APPLY_PPB; if (p1 > hw) p1 = hw;
   gn_apply_block<TI, TO>(x0, c0, ld0, x1, c1, ld1, st0, st0_ld, st1, st1_ld, gamma, beta, gb_bstride, out, ld_out, hw, groups, eps, act,
-                         p0, p1, s_mean, s_rstd);
+                         p0, p1, s_mean, s_rstd, b);
 }
 
 // ---------------------------------------------------------------------------------
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(256, 3) gn_l2_kernel(const T* __restrict__ x0,
   const int64_t p0 = (int64_t)blockIdx.x * GN_PPB;
   int64_t p1 = p0 + GN_PPB; if (p1 > hw) p1 = hw;
   gn_apply_block<T, T>(x0, c0, ld0, x1, c1, ld1, st0, st0_ld, st1, st1_ld, gamma, beta, gb_bstride, out, ld_out, hw, groups, eps, act,
-                       p0, p1, s_mean, s_rstd);
+                       p0, p1, s_mean, s_rstd, b);
   // every block of the image has read the flag and the statistics once it arrives here: the last arrival resets them
   __syncthreads();
   if (threadIdx.x == 0) {
