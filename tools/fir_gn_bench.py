@@ -27,4 +27,4 @@ for C, S, up in shapes:
     ts.sort()
     t = ts[len(ts) // 2]
     gb = (x.numel() + h.numel() + xr.numel()) * 2 / 1e9
-    print(f"C={C:3d} {S}^2 {'up  ' if up else 'down'}: {t * 1e3:8.1f} us  {gb:6.3f} GB  {gb / t:7.1f} GB/s ... {gb / t / 6.54:5.1f}% of 6540")
+    print(f"C={C:3d} {S}^2 {'up  ' if up else 'down'}: {t * 1e3:8.1f} us  {gb:6.3f} GB  {gb / t:6.2f} TB/s = {100 * gb / t / 6.54:5.1f}% of the 6.54 TB/s HBM copy peak")
