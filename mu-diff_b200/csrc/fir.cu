@@ -414,7 +414,9 @@ int launch_fir4_quad_gn(const void* in, void* out_h, void* out_x, const float* k
 // stages the input tile (+ FIR halo) of a 32-channel chunk ONCE: raw x and h = act(x * scale + shift) rounded to bf16 (exactly
 // what the stand-alone GroupNorm pass stores), then every thread filters 2 (down) / 2 x 4 (up) outputs of one 16-byte channel
 // vector from shared memory.  DOWN: 8 x 16 outputs from 18 x 34 inputs (76.5 KB, two CTAs per SM; pixel slots swizzled so
-// that the stride-2 window reads are bank-conflict free); UP: 16 x 32 outputs from 10 x 18 inputs.
+// that the stride-2 window reads are bank-conflict free); UP: 16 x 32 outputs from 10 x 18 inputs, three CTAs per SM (write-bound:
+// 618 -> 520 us for 128 channels at 128^2 against two CTAs; filtering x and h in two passes over ONE tile buffer - four CTAs per
+// SM - was slower, 579 us, and did not move the instruction-bound down-sampling case).
 constexpr int kFirCC = 32;
 template <int UP, int DOWN> struct FirTile {
   static constexpr int OTH = DOWN == 2 ? 8 : 16, OTW = DOWN == 2 ? 16 : 32;
@@ -437,7 +439,7 @@ __device__ __forceinline__ uint4 pack_bf16x8(const f32x2 (&v)[4]) {
 }
 
 template <int UP, int DOWN>
-__global__ void __launch_bounds__(256, 2) fir4_tile_gn_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out_h,
+__global__ void __launch_bounds__(256, UP == 2 ? 3 : 2) fir4_tile_gn_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out_h,
                                                            __nv_bfloat16* __restrict__ out_x, const float* __restrict__ kern,
                                                            const float* __restrict__ table, int table_ld, int act, FirP p,
                                                            int tiles_x, int tiles_y, int cchunks) {
