@@ -960,7 +960,10 @@ extern "C" int mudiff_stem_conv_tc(const float* x, const float* wt, const float*
     if (e != cudaSuccess) return (int)e;
     attr_set[dev][which] = true;
   }
-  const int grid = (int)(p.total_units < MUDIFF_NUM_SMS ? p.total_units : MUDIFF_NUM_SMS);
+  static int per_sm = 0;
+  if (!per_sm) { const char* e = getenv("MUDIFF_STEM_TC_CTAS"); per_sm = e ? atoi(e) : 2; if (per_sm < 1) per_sm = 1; }
+  const long long gmax = (long long)MUDIFF_NUM_SMS * per_sm;
+  const int grid = (int)(p.total_units < gmax ? p.total_units : gmax);
   cudaStream_t st = (cudaStream_t)stream;
   if (which) stem_tc_kernel<true><<<grid, 288, kStemSmem, st>>>(p);
   else stem_tc_kernel<false><<<grid, 288, kStemSmem, st>>>(p);

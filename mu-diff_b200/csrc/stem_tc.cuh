@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t bf16_hi_lo_pack(float v, float& lo_out) {
 }
 
 template <bool kOutF32>
-__global__ void __launch_bounds__(288, 1) stem_tc_kernel(const __grid_constant__ StemTcP p) {
+__global__ void __launch_bounds__(288, 2) stem_tc_kernel(const __grid_constant__ StemTcP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint8_t* bar_block = smem + kStemBar;
