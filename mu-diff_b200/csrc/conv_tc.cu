@@ -756,6 +756,7 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   // the epilogue is then not overlapped with the next unit's MMAs (tools/conv_bench.py, N = 384, K = 1728: 1243 TFLOP/s, 1755
   // without the epilogue).  128-column tiles keep two stages: gate conv 20.3 -> 15.6 ms per bench step.  Flag 0x400000: old plan.
   if (!(d->flags & 0x400000) && n_tile > 128 && n_tile < 256 && d->n % 128 == 0) n_tile = 128;
+  p.n_tile = n_tile; p.n_tiles = d->n / n_tile; p.n_total = d->n;
   // A staging: halo whenever a 3x3 segment exists and the image is at least one 8x2 patch
   bool halo = any9 && d->w >= 8 && d->h >= 2 && !(d->flags & 2);
   if (halo) { p.tile_w = 8; p.tile_h = 16; }
@@ -765,13 +766,6 @@ int plan_conv(const mudiff_conv_desc* d, TcParams& p, int& ktot_out) {
   p.tiles_x = (d->w + p.tile_w - 1) / p.tile_w;
   const int tiles_y = (d->h + p.tile_h - 1) / p.tile_h;
   p.tpi = p.tiles_x * tiles_y;
-  // Small launches (a batch-1 conv at the 64^2 level is 32 pixel tiles): with one wide N tile only a fifth of the SMs would
-  // work, each through the whole K loop.  Narrower N tiles spread the launch over more CTAs (the column partition does not
-  // change any output bit); the A tiles are re-read per N tile from L2, which is irrelevant at this size.  Flag 0x800000: off.
-  if (!(d->flags & 0x800000) && !d->w_bstride) {
-    while (n_tile >= 128 && n_tile % 64 == 0 && (long long)d->batch * p.tpi * (d->n / n_tile) < MUDIFF_NUM_SMS / 2) n_tile /= 2;
-  }
-  p.n_tile = n_tile; p.n_tiles = d->n / n_tile; p.n_total = d->n;
   p.nseg = d->nseg;
   p.a_batched = d->a_batched ? 1 : 0;
   p.w_batched = d->w_bstride != 0 ? 1 : 0;

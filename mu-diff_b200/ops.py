@@ -17,7 +17,6 @@ import os as _os
 _ENV_FLAGS = 2 if _os.environ.get('MUDIFF_HALO', '1') == '0' else 0     # debug knob: forbid halo staging
 _ENV_FLAGS |= int(_os.environ.get('MUDIFF_XF_DBG', '0')) << 20        # timing ablations of the operand transform
 _ENV_FLAGS |= 1024 if _os.environ.get('MUDIFF_BCAP12', '0') == '1' else 0   # ablation: the older, larger B ring (12 sub-tiles)
-_ENV_FLAGS |= 0x800000 if _os.environ.get('MUDIFF_SMALL_SPLIT_N', '1') == '0' else 0   # ablation: keep wide N tiles on small launches
 _ENV_FLAGS |= 0x400000 if _os.environ.get('MUDIFF_NT128', '1') == '0' else 0   # ablation: N = 384 as two 192-column tiles (one accumulator stage) instead of three of 128
 
 # Fused epilogue statistics (conv_tc butterfly reduction) are implemented and tested, but since the MMA issue
