@@ -17,7 +17,7 @@ Prints ONE JSON line (rank 0).  Keys: see the driver contract; additionally
   e2e          : same metric through the public API with pinned-host inputs -> H2D -> device RNG ->
                  graph replay -> D2H of the synthesized slices, every step.
   volume       : BASELINE configs[2] shape through volume.predict_volumes_sharded: 8 volumes x 155 axial slices x 256^2,
-                 slices sharded over the N ranks, one CUDA graph per rank at the balanced shard batch, ONE NCCL
+                 slices sharded over the N ranks, batches packed across volumes, one CUDA graph per rank, ONE NCCL
                  all-gather per volume (the path's only collective); slices/s = all slices / max-over-ranks time
   other_configs: (N = 1) short device-resident timings of BASELINE configs[0] (B = 1), [3] (healthy, B = 128), the corners of
                  [4] (128^2, 512^2), nf = 128 and the fp32 path - so that they are in the driver's record
@@ -228,8 +228,8 @@ def workload_config(args):
 
 def volume_record(args, M, cfg, co, g1, g2, dev, world, rank):
     """BASELINE configs[2]: `--volumes` synthetic volumes x 155 axial slices x 256^2 through
-    volume.predict_volumes_sharded - contiguous slice shards per rank, one CUDA graph per rank at the balanced shard
-    batch, per-slice RNG streams, pinned host conditioning slices (H2D inside the timed region), ONE all-gather per
+    volume.predict_volumes_sharded - contiguous slice shards per rank, batches packed across volumes, one CUDA graph per
+    rank at the balanced batch, per-slice RNG streams, pinned host conditioning slices (H2D inside the timed region), ONE all-gather per
     volume.  Time = max over ranks of the wall clock between two barriers + synchronizes."""
     import hashlib
     import torch
@@ -237,7 +237,9 @@ def volume_record(args, M, cfg, co, g1, g2, dev, world, rank):
     from mudiff_b200 import volume as V
     n_slices, S = 155, args.size
     per_rank = (n_slices + world - 1) // world
-    gbatch = V.balanced_batch(per_rank, args.batch)
+    # batches are packed across volume boundaries (volume.predict_volumes_sharded pack=True): the graph batch balances the
+    # rank's slices of ALL volumes of the run (8 x 20 = 160 -> three batches of 54 at 8 ranks, not eight batches of 20)
+    gbatch = V.balanced_batch(per_rank * args.volumes, args.batch)
     sampler = V.GraphSliceSampler(co, g1, g2, cfg.num_timesteps, gbatch, S, cfg.nz, n_cond=3, device=dev)
     gen = torch.Generator().manual_seed(4242)
     conds = [(torch.randn(n_slices, 1, S, S, generator=gen).clamp(-3, 3) / 3).pin_memory() for _ in range(3)]

@@ -129,3 +129,24 @@ def test_balanced_batch():
         b = V.balanced_batch(n, 64)
         k = -(-n // b)
         assert b <= 64 and k == -(-n // 64) and k * b - n < k       # same number of batches, < 1 padded row per batch
+
+
+def test_packed_batches_fill_across_volumes():
+    """pack=True: a rank's batches are filled across volume boundaries (one batch of `batch` slices instead of one short batch
+    per volume), pack=False keeps one batch per (volume, range); both give identical volumes (per-slice RNG streams)."""
+    import mudiff_b200.volume as V
+    vols = _make_volumes([5, 5, 5, 3, 7])
+    sizes = {True: [], False: []}
+
+    def sampler_for(flag):
+        def f(conds, x_init, latents, noises):
+            sizes[flag].append(x_init.shape[0])
+            return _fake_sampler(conds, x_init, latents, noises)
+        return f
+
+    kw = dict(seed=11, first_volume=4, nz=10, n_time=4, batch=8, device='cpu')
+    packed = V.predict_volumes_sharded(sampler_for(True), vols, pack=True, **kw)
+    plain = V.predict_volumes_sharded(sampler_for(False), vols, pack=False, **kw)
+    assert sizes[True] == [8, 8, 8, 1] and sizes[False] == [5, 5, 5, 3, 7]
+    for a, b in zip(packed, plain):
+        np.testing.assert_array_equal(a.numpy(), b.numpy())
