@@ -254,7 +254,10 @@ def volume_record(args, M, cfg, co, g1, g2, dev, world, rank):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    run(1)                                        # warm-up: NCCL channel set-up, allocator, graph replay
+    # warm-up: NCCL channel set-up, graph replay, and the caching allocator at the shapes of the timed run - enough volumes
+    # for at least one FULL packed batch (at 8 ranks a single volume gives a 20-slice batch, the timed run 54-slice ones:
+    # the cudaMallocs of the larger blocks cost 0.5 s of the 1.4 s when they fell into the timed region)
+    run(min(args.volumes, (gbatch + per_rank - 1) // per_rank + 1))
     sync()
     t0 = time.perf_counter()
     full = run(args.volumes)[-1]

@@ -243,11 +243,15 @@ def predict_volumes_sharded(sample_fn: Callable, cond_volumes: Sequence[Sequence
             locals_[v][b0 - lo:b1 - lo] = fake01[off:off + (b1 - b0)]
             off += b1 - b0
         nxt = prepare(items[i + 1]) if i + 1 < len(items) else None        # overlaps the sampling just enqueued
-        # every volume whose last piece is in this batch (and the volumes before it of which this rank owns nothing)
-        v_done = max(v for v, _, _ in item if last_item_of[v] == i) if any(last_item_of[v] == i for v, _, _ in item) else -1
-        while done_upto <= v_done:
-            finish(done_upto)
-            done_upto += 1
+        # every volume whose last piece is in this batch (and the volumes before it of which this rank owns nothing).  With
+        # packed batches the ranks' batch boundaries fall on different volumes, and an all-gather issued between two batches
+        # on the compute stream makes a rank wait for peers that are still one batch behind (8 ranks: 1.39 s instead of
+        # 0.9 s for 8 volumes): the gathers are then issued after the rank's last batch, still one per volume, in volume order.
+        if not (pack and world > 1 and gather):
+            v_done = max((v for v, _, _ in item if last_item_of[v] == i), default=-1)
+            while done_upto <= v_done:
+                finish(done_upto)
+                done_upto += 1
     while done_upto < len(cond_volumes):
         finish(done_upto)
         done_upto += 1
