@@ -469,74 +469,97 @@ __global__ void stem_scale_shift_kernel(const double* __restrict__ moments, cons
   }
 }
 
-// conv3x3(1 -> N) * scale[b][c] + shift[b][c] -> activation; structure of conv_stem_kernel with per-image folded weights.
+// conv3x3(1 -> N) * scale[b][c] + shift[b][c] -> activation, per-image folded weights (a thread owns 8 output channels: 72
+// weights + 8 biases as FFMA2 pairs in registers) and walks pixel pairs of a row.  The input rows live in a shared-memory RING
+// of four zero-padded rows (one new row per output row, one __syncthreads per row): the first version gathered its 3 x 4 window
+// per pixel pair from global memory with bounds checks and 64-bit address arithmetic - 288 instructions per pair of which only
+// 126 did arithmetic, loads or stores (cuobjdump); here the window is six 8-byte LDS with immediate offsets.  For SiLU outputs
+// the 1/2 of silu(t) = h + h tanh(h), h = t / 2, is folded into the weights (bf16 path).
 template <typename TO>
 __global__ void __launch_bounds__(256, 2) conv_stem_gn_kernel(SimtP p, const float* __restrict__ scale_shift) {
+  extern __shared__ float s_rows[];                       // [4][wp]: row slot (y & 3); s[1 + x] = x-th pixel, s[0] = s[W + 1] = 0
   const int nv = p.n / 8;
   const int n0 = (threadIdx.x % nv) * 8;
   const int lane = threadIdx.x / nv, lanes = blockDim.x / nv;
-  if (lane >= lanes) return;
+  const bool worker = lane < lanes;
   const float* wt = (const float*)p.wt;
   const int ld = p.a_ld[0];
   const int W = p.w, H = p.h;
+  const int wp = (W + 2 + 3) & ~3;
   const int64_t rows = (int64_t)p.batch * H;
-  f32x2 w2[9][4], bs2[4];                       // channel pairs (n0 + 2j, n0 + 2j + 1): FFMA2
+  const bool fold = p.act == MUDIFF_ACT_SILU && sizeof(TO) == 2;
+  const float hf = fold ? 0.5f : 1.f;
+  f32x2 w2[9][4], bs2[4];                                 // channel pairs (n0 + 2j, n0 + 2j + 1): FFMA2
   int cur_b = -1;
-  for (int64_t row = (int64_t)blockIdx.x * STEM_ROWS; row < rows && row < (int64_t)(blockIdx.x + 1) * STEM_ROWS; ++row) {
+  const int64_t row0 = (int64_t)blockIdx.x * STEM_ROWS;
+  for (int64_t row = row0; row < rows && row < row0 + STEM_ROWS; ++row) {
     const int b = (int)(row / H), y = (int)(row - (int64_t)b * H);
-    if (b != cur_b) {
+    const bool fresh = b != cur_b;                        // first row of this block in image b: stage rows y - 1, y, y + 1
+    if (fresh) {
+      if (cur_b >= 0) __syncthreads();                    // image boundary inside the block: all three slots are rewritten
       cur_b = b;
+      if (worker) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = n0 + 2 * j;
-        const float4 ss = *reinterpret_cast<const float4*>(scale_shift + ((int64_t)b * p.n + c) * 2);   // sc0 sh0 sc1 sh1
+        for (int j = 0; j < 4; ++j) {
+          const int c = n0 + 2 * j;
+          const float4 ss = *reinterpret_cast<const float4*>(scale_shift + ((int64_t)b * p.n + c) * 2);   // sc0 sh0 sc1 sh1
 #pragma unroll
-        for (int t = 0; t < 9; ++t) w2[t][j] = pack2(wt[c * 9 + t] * ss.x, wt[(c + 1) * 9 + t] * ss.z);
-        bs2[j] = pack2((p.bias ? p.bias[c] : 0.f) * ss.x + ss.y, (p.bias ? p.bias[c + 1] : 0.f) * ss.z + ss.w);
+          for (int t = 0; t < 9; ++t) w2[t][j] = pack2(wt[c * 9 + t] * ss.x * hf, wt[(c + 1) * 9 + t] * ss.z * hf);
+          bs2[j] = pack2(((p.bias ? p.bias[c] : 0.f) * ss.x + ss.y) * hf, ((p.bias ? p.bias[c + 1] : 0.f) * ss.z + ss.w) * hf);
+        }
       }
     }
     const float* in = (const float*)p.a[0] + (int64_t)b * H * W * ld;
-    const float* r0 = y > 0 ? in + (int64_t)(y - 1) * W * ld : nullptr;
-    const float* r1 = in + (int64_t)y * W * ld;
-    const float* r2 = y + 1 < H ? in + (int64_t)(y + 1) * W * ld : nullptr;
-    // software pipeline: the 3x4 input window of the NEXT pixel pair is loaded before the current pair is computed (the
-    // kernel runs at 16 warps per SM - 110 registers of per-thread weights - so nothing else hides the load latency)
-    auto load_win = [&](float (&v)[3][4], int x) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int ix = x - 1 + c;
-        const bool okx = ix >= 0 && ix < W;
-        v[0][c] = (okx && r0) ? __ldg(r0 + (int64_t)ix * ld) : 0.f;
-        v[1][c] = okx ? __ldg(r1 + (int64_t)ix * ld) : 0.f;
-        v[2][c] = (okx && r2) ? __ldg(r2 + (int64_t)ix * ld) : 0.f;
-      }
-    };
-    float v[3][4];
-    if (lane * 2 < W) load_win(v, lane * 2);
+    for (int yy = fresh ? y - 1 : y + 1; yy <= y + 1; ++yy) {
+      float* dst = s_rows + ((yy + 4) & 3) * wp;
+      const bool inside = yy >= 0 && yy < H;
+      const float* src = in + (int64_t)yy * W * ld;
+      for (int i = threadIdx.x; i < wp; i += blockDim.x)
+        dst[i] = (inside && i >= 1 && i <= W) ? __ldg(src + (int64_t)(i - 1) * ld) : 0.f;
+    }
+    __syncthreads();          // the ring has four slots: the slot written for row y + 2 is not among the three read for row y + 1
+    if (!worker) continue;
+    const float* r0 = s_rows + ((y + 3) & 3) * wp;        // row y - 1
+    const float* r1 = s_rows + (y & 3) * wp;
+    const float* r2 = s_rows + ((y + 1) & 3) * wp;
     for (int x = lane * 2; x < W; x += lanes * 2) {
-      float vn[3][4];
-      if (x + lanes * 2 < W) load_win(vn, x + lanes * 2);
-      float xp[9][2];                            // taps of the two pixels, copied out so that v can be overwritten
-#pragma unroll
-      for (int t = 0; t < 9; ++t) { xp[t][0] = v[t / 3][t % 3]; xp[t][1] = v[t / 3][t % 3 + 1]; }
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[r][c] = vn[r][c];
+      // window columns x - 1 .. x + 2 = s[x .. x + 3] (x even: two aligned float2 per row)
+      float v[3][4];
+      {
+        const float2 a0 = *reinterpret_cast<const float2*>(r0 + x), a1 = *reinterpret_cast<const float2*>(r0 + x + 2);
+        const float2 b0 = *reinterpret_cast<const float2*>(r1 + x), b1 = *reinterpret_cast<const float2*>(r1 + x + 2);
+        const float2 c0 = *reinterpret_cast<const float2*>(r2 + x), c1 = *reinterpret_cast<const float2*>(r2 + x + 2);
+        v[0][0] = a0.x; v[0][1] = a0.y; v[0][2] = a1.x; v[0][3] = a1.y;
+        v[1][0] = b0.x; v[1][1] = b0.y; v[1][2] = b1.x; v[1][3] = b1.y;
+        v[2][0] = c0.x; v[2][1] = c0.y; v[2][2] = c1.x; v[2][3] = c1.y;
+      }
 #pragma unroll
       for (int px = 0; px < 2; ++px) {
         if (x + px >= W) break;
-        float acc[8];
+        f32x2 a[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          f32x2 a = bs2[j];
+        for (int j = 0; j < 4; ++j) a[j] = bs2[j];
 #pragma unroll
-          for (int t = 0; t < 9; ++t) { const float xv = xp[t][px]; a = fma2(pack2(xv, xv), w2[t][j], a); }
-          unpack2(a, acc[2 * j], acc[2 * j + 1]);
+        for (int t = 0; t < 9; ++t) {
+          const float xv = v[t / 3][t % 3 + px];
+          const f32x2 xx = pack2(xv, xv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] = fma2(xx, w2[t][j], a[j]);
         }
-        if (p.act == MUDIFF_ACT_SILU) {
+        float acc[8];
+        if (fold) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = (sizeof(TO) == 4) ? silu_exact(acc[j]) : silu_f(acc[j]);
+          for (int j = 0; j < 4; ++j) {
+            float h0, h1; unpack2(a[j], h0, h1);
+            unpack2(fma2(a[j], pack2(tanh_approx(h0), tanh_approx(h1)), a[j]), acc[2 * j], acc[2 * j + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) unpack2(a[j], acc[2 * j], acc[2 * j + 1]);
+          if (p.act == MUDIFF_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = silu_exact(acc[j]);
+          }
         }
         const int64_t pix = row * W + x + px;
         TO* op = (TO*)p.out + pix * p.out_ld + p.out_coff + n0;
@@ -834,8 +857,10 @@ extern "C" int mudiff_stem_conv_gn_act(const float* x, int ld, const float* wt, 
   const int nv = n / 8;
   const int block = (256 / nv) * nv;
   const unsigned grid = (unsigned)((rows + STEM_ROWS - 1) / STEM_ROWS);
-  if (out_dtype == MUDIFF_BF16) conv_stem_gn_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(p, scale_shift);
-  else if (out_dtype == MUDIFF_F32) conv_stem_gn_kernel<float><<<grid, block, 0, st>>>(p, scale_shift);
+  const size_t smem = 4 * (size_t)((w + 2 + 3) & ~3) * sizeof(float);          // ring of four padded input rows
+  if (smem > 48 * 1024) return MUDIFF_EUNSUPPORTED;
+  if (out_dtype == MUDIFF_BF16) conv_stem_gn_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(p, scale_shift);
+  else if (out_dtype == MUDIFF_F32) conv_stem_gn_kernel<float><<<grid, block, smem, st>>>(p, scale_shift);
   else return MUDIFF_EUNSUPPORTED;
   return mudiff_launch_status();
 }
