@@ -243,6 +243,39 @@ def test_full_size_256_bf16_and_fp32_vs_oracle(M):
         assert torch.equal(xg, x3)                                # graph replay == eager, bit for bit
 
 
+def test_streaming_sampler_equals_sequential(M):
+    """sampling.StreamingSampler (H2D / D2H of neighbouring batches overlapped with the graph replay on copy streams):
+    five different host batches, the last one ragged, give bit for bit what the sequential copy -> draw -> replay -> copy
+    loop gives with the same device RNG stream (a staging-slot race would show as a mismatch)."""
+    cfg = O.default_config(num_channels_dae=64, image_size=64)
+    ns, g1, g2, _, _ = _build(M, cfg, 'bf16')
+    co = M.Posterior_Coefficients(ns, DEV)
+    B, S = 4, 64
+    gs = M.GraphSampler(co, g1, g2, cfg.num_timesteps, B, S, cfg.nz, n_cond=3, device=DEV)
+    gen = torch.Generator().manual_seed(11)
+    sizes = [4, 4, 4, 4, 3]
+    batches = [[torch.randn(n, 1, S, S, generator=gen).clamp(-3, 3).div(3).pin_memory() for _ in range(3)] for n in sizes]
+
+    dgen = torch.Generator(device=DEV).manual_seed(77)
+    ss = M.StreamingSampler(gs, generator=dgen)
+    want = []
+    for conds in batches:                                   # sequential reference: one batch at a time, fully synchronised
+        n = conds[0].shape[0]
+        for d, h in zip(gs.conds, conds):
+            d[:n].copy_(h)
+        ss.draw_noise()
+        want.append(gs.replay()[:n].cpu())
+        torch.cuda.synchronize()
+    dgen.manual_seed(77)
+    outs = [torch.empty(n, 1, S, S).pin_memory() for n in sizes]
+    for conds, o in zip(batches, outs):
+        ss.submit(conds, o)
+    ss.synchronize()
+    for w, o in zip(want, outs):
+        assert torch.equal(w, o)
+    assert not torch.equal(outs[0], outs[1])
+
+
 def test_validation_sampler_follows_weight_updates(M):
     """validation.ValidationSampler, alias mode: the fast modules alias the training modules' weights; after an in-place
     update (an optimiser step) the packed copies are refreshed IN PLACE and the SAME captured graph gives the eager result
