@@ -16,8 +16,20 @@ SHAPES = [  # (H, Cin list, taps, N)
     (64, [256], [9], 256),
     (64, [512], [9], 256),
     (256, [192], [9], 384),
+    (256, [320], [9], 64),
+    (256, [192], [9], 64),
+    (256, [128], [9], 64),
+    (256, [256, 64], [9, 9], 64),
+    (256, [384], [9], 64),
+    (256, [448], [9], 64),
+    (256, [512], [9], 64),
+    (128, [320], [9], 128),
+    (128, [384], [9], 128),
 ]
-VARIANTS = [('default', 0), ('pair+dry', 64), ('pair+noepi', 128), ('pair+dry+noepi', 192), ('single', 0x4000), ('single+nostore', 0x4000 + 2048), ('single+noldtm', 0x4000 + 4096), ('single+noepi', 0x4000 + 128), ('single+dry', 0x4000 + 64), ('single+dry+noepi', 0x4000 + 192), ('single+mt1', 0x4000 + 16)]
+if os.environ.get('CB_VARIANTS') == 'short':
+    VARIANTS = [('default', 0), ('dry', 64), ('dry+noepi', 192), ('mt1', 16), ('mt1+dry+noepi', 16 + 192), ('nohalo', 2), ('nohalo+dry+noepi', 2 + 192)]
+else:
+  VARIANTS = [('default', 0), ('pair+dry', 64), ('pair+noepi', 128), ('pair+dry+noepi', 192), ('single', 0x4000), ('single+nostore', 0x4000 + 2048), ('single+noldtm', 0x4000 + 4096), ('single+noepi', 0x4000 + 128), ('single+dry', 0x4000 + 64), ('single+dry+noepi', 0x4000 + 192), ('single+mt1', 0x4000 + 16)]
 if os.environ.get('CB_SHAPES'):
     SHAPES = [SHAPES[int(i)] for i in os.environ['CB_SHAPES'].split(',')]
 
