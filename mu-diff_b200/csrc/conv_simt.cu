@@ -20,6 +20,7 @@ struct SimtP {
   const void* residual; int res_ld;
   float alpha, beta; int act;
   void* out; int out_ld, out_coff;
+  int rpb;                                   // stem kernels: image rows per block (launch shape only, see stem_rpb)
 };
 
 template <typename TO>
@@ -215,6 +216,13 @@ __global__ void __launch_bounds__(256) conv_small_k_kernel(SimtP p) {
 
 // ---------------------------------------------------------------------------------
 #define STEM_ROWS 8
+// rows per block of the stem kernels: STEM_ROWS for large launches; fewer when the launch would not fill the SMs (a batch-1
+// 256^2 image is 32 blocks of 8 rows - 28 us for a kernel whose work is 2 - 3 us; with one row per block it is 256 blocks).
+// Every output pixel is computed by the same instruction sequence whatever the block shape: results are identical.
+static inline int stem_rpb(int64_t rows) {
+  int64_t r = rows / (2 * MUDIFF_NUM_SMS);
+  return (int)(r < 1 ? 1 : (r > STEM_ROWS ? STEM_ROWS : r));
+}
 // stem kernel: Cin == 1, 3x3 pad 1, stride 1, N % 8 == 0 (the 1->nf ConvFeatBlock convs).
 // HBM-write bound in principle (9 MACs per output) but FFMA/issue bound in practice, so every thread
 // computes TWO adjacent pixels x 8 output channels from one 3x4 input patch (12 loads for 144 FMAs; the 72
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(SimtP p) {
   const int ld = p.a_ld[0];
   const int W = p.w, H = p.h;
   const int64_t rows = (int64_t)p.batch * H;
-  for (int64_t row = (int64_t)blockIdx.x * STEM_ROWS; row < rows && row < (int64_t)(blockIdx.x + 1) * STEM_ROWS; ++row) {
+  for (int64_t row = (int64_t)blockIdx.x * p.rpb; row < rows && row < (int64_t)(blockIdx.x + 1) * p.rpb; ++row) {
     const int b = (int)(row / H), y = (int)(row - (int64_t)b * H);
     float rb[8];
 #pragma unroll
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(256) conv_stem_s2_kernel(SimtP p) {
   const int ld = p.a_ld[0];
   const int W = p.w, H = p.h, WO = p.wo, HO = p.ho;
   const int64_t rows = (int64_t)p.batch * HO;
-  for (int64_t row = (int64_t)blockIdx.x * STEM_ROWS; row < rows && row < (int64_t)(blockIdx.x + 1) * STEM_ROWS; ++row) {
+  for (int64_t row = (int64_t)blockIdx.x * p.rpb; row < rows && row < (int64_t)(blockIdx.x + 1) * p.rpb; ++row) {
     const int b = (int)(row / HO), y = (int)(row - (int64_t)b * HO);
     const float* in = (const float*)p.a[0] + ((int64_t)b * H + 2 * y) * W * ld;
     for (int x = lane; x < WO; x += lanes) {
@@ -491,8 +499,8 @@ __global__ void __launch_bounds__(256, 2) conv_stem_gn_kernel(SimtP p, const flo
   const float hf = fold ? 0.5f : 1.f;
   f32x2 w2[9][4], bs2[4];                                 // channel pairs (n0 + 2j, n0 + 2j + 1): FFMA2
   int cur_b = -1;
-  const int64_t row0 = (int64_t)blockIdx.x * STEM_ROWS;
-  for (int64_t row = row0; row < rows && row < row0 + STEM_ROWS; ++row) {
+  const int64_t row0 = (int64_t)blockIdx.x * p.rpb;
+  for (int64_t row = row0; row < rows && row < row0 + p.rpb; ++row) {
     const int b = (int)(row / H), y = (int)(row - (int64_t)b * H);
     const bool fresh = b != cur_b;                        // first row of this block in image b: stage rows y - 1, y, y + 1
     if (fresh) {
@@ -587,7 +595,7 @@ __global__ void __launch_bounds__(256, 2) conv_stem_gn_kernel(SimtP p, const flo
 #define HEAD_YR 32
 #define HEAD_COLS 30
 template <typename TA, typename TO>
-__global__ void __launch_bounds__(256, 2) conv_head_kernel(SimtP p, int xchunks, int ystrips) {
+__global__ void __launch_bounds__(256, 2) conv_head_kernel(SimtP p, int xchunks, int ystrips, int yr) {
   constexpr int V = 16 / sizeof(TA);          // 8 (bf16) or 4 (fp32) channels per 16-byte load
   constexpr int PB = 64 * sizeof(TA);         // bytes of one 64-channel block of a pixel: 128 / 256
   constexpr int NV = PB / 16;                 // 16-byte vectors per pixel block: 8 / 16
@@ -606,8 +614,8 @@ __global__ void __launch_bounds__(256, 2) conv_head_kernel(SimtP p, int xchunks,
   const int ys = (int)((unit / xchunks) % ystrips);
   const int b = (int)(unit / ((int64_t)xchunks * ystrips));
   const int x0 = xc * HEAD_COLS;                 // first output column of this warp
-  const int y0 = ys * HEAD_YR;
-  const int y1 = min(y0 + HEAD_YR, p.h);
+  const int y0 = ys * yr;
+  const int y1 = min(y0 + yr, p.h);
   const int ld = p.a_ld[0];
   const TA* in = (const TA*)p.a[0] + (int64_t)b * p.h * p.w * ld;
   const int nblk = C / 64;
@@ -700,7 +708,8 @@ int launch_simt(const SimtP& p, cudaStream_t st) {
         (p.out_ld % 8 == 0) && (p.out_coff % 8 == 0)) {
       const int nv = p.n / 8;
       int block = (256 / nv) * nv;
-      conv_stem_kernel<TO><<<(unsigned)((rows + STEM_ROWS - 1) / STEM_ROWS), block, 0, st>>>(p);
+      SimtP q = p; q.rpb = stem_rpb(rows);
+      conv_stem_kernel<TO><<<(unsigned)((rows + q.rpb - 1) / q.rpb), block, 0, st>>>(q);
       return mudiff_launch_status();
     }
   }
@@ -711,14 +720,20 @@ int launch_simt(const SimtP& p, cudaStream_t st) {
       const int block = (256 / nv) * nv;
       const int64_t orows = (int64_t)p.batch * p.ho;
       if (orows < (1LL << 31)) {
-        conv_stem_s2_kernel<TO><<<(unsigned)((orows + STEM_ROWS - 1) / STEM_ROWS), block, 0, st>>>(p);
+        SimtP q = p; q.rpb = stem_rpb(orows);
+        conv_stem_s2_kernel<TO><<<(unsigned)((orows + q.rpb - 1) / q.rpb), block, 0, st>>>(q);
         return mudiff_launch_status();
       }
     }
   }
   if (plain && s1 && p.n == 1 && p.a_c[0] % 64 == 0 && p.a_c[0] <= 512 && p.a_ld[0] % (16 / (int)sizeof(TA)) == 0 &&
       ((uintptr_t)p.a[0] % 16 == 0)) {
-    const int xchunks = (p.w + HEAD_COLS - 1) / HEAD_COLS, ystrips = (p.h + HEAD_YR - 1) / HEAD_YR;
+    // strip height: HEAD_YR rows per warp for large launches (a strip re-reads two halo rows), fewer when the launch would not
+    // fill the SMs (batch 1 at 256^2: 9 blocks, 99 us; with 4-row strips 72 blocks).  Identical results for any height.
+    const int xchunks = (p.w + HEAD_COLS - 1) / HEAD_COLS;
+    int yr = (int)(((int64_t)p.batch * p.h * xchunks) / (8 * 2 * MUDIFF_NUM_SMS));
+    yr = yr < 2 ? 2 : (yr > HEAD_YR ? HEAD_YR : yr);
+    const int ystrips = (p.h + yr - 1) / yr;
     const int64_t units = (int64_t)p.batch * ystrips * xchunks;
     const int64_t blocks = (units + 7) / 8;
     if (blocks < (1LL << 31)) {
@@ -730,7 +745,7 @@ int launch_simt(const SimtP& p, cudaStream_t st) {
           return (int)cudaGetLastError();
         done = true;
       }
-      conv_head_kernel<TA, TO><<<(unsigned)blocks, 256, smem, st>>>(p, xchunks, ystrips);
+      conv_head_kernel<TA, TO><<<(unsigned)blocks, 256, smem, st>>>(p, xchunks, ystrips, yr);
       return mudiff_launch_status();
     }
   }
@@ -856,7 +871,8 @@ extern "C" int mudiff_stem_conv_gn_act(const float* x, int ld, const float* wt, 
   p.out = out; p.out_ld = out_ld; p.out_coff = out_coff;
   const int nv = n / 8;
   const int block = (256 / nv) * nv;
-  const unsigned grid = (unsigned)((rows + STEM_ROWS - 1) / STEM_ROWS);
+  p.rpb = stem_rpb(rows);
+  const unsigned grid = (unsigned)((rows + p.rpb - 1) / p.rpb);
   const size_t smem = 4 * (size_t)((w + 2 + 3) & ~3) * sizeof(float);          // ring of four padded input rows
   if (smem > 48 * 1024) return MUDIFF_EUNSUPPORTED;
   if (out_dtype == MUDIFF_BF16) conv_stem_gn_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(p, scale_shift);
