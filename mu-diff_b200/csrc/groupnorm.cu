@@ -27,7 +27,8 @@ static inline int gn_ppb(int64_t hw, int C) {
 template <typename T>
 __device__ __forceinline__ bool gn_stats_block(const T* __restrict__ x0, int c0, int ld0, const T* __restrict__ x1, int c1, int ld1,
                                                int64_t hw, int groups, double* stats, int st_ld, int st_off,
-                                               double* partial, unsigned int* tickets, int GN_PPB, float* s_part, bool* s_last) {
+                                               double* partial, unsigned int* tickets, int GN_PPB, float* s_part, bool* s_last,
+                                               double* s_tot = nullptr) {
   constexpr int V = 16 / sizeof(T);
   const int C = c0 + c1;
   const int cv = C / V;
@@ -109,6 +110,13 @@ __device__ __forceinline__ bool gn_stats_block(const T* __restrict__ x0, int c0,
     const int k0 = sg * cps, k1 = (k0 + cps < chunks) ? k0 + cps : chunks;
     double a = 0.0;
     int k = k0;
+    for (; k + 16 <= k1; k += 16) {                        // one L2 round trip for the usual 32 chunks x 2 runs (same order of adds)
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = __ldcg(pb + (int64_t)(k + u) * nvals + i);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) a += v[u];
+    }
     for (; k + 8 <= k1; k += 8) {
       double v[8];
 #pragma unroll
@@ -124,6 +132,7 @@ __device__ __forceinline__ bool gn_stats_block(const T* __restrict__ x0, int c0,
     double a = 0.0;
     for (int sg = 0; sg < segs; ++sg) a += s_run[(size_t)sg * nvals + i];
     stats[((int64_t)b * st_ld + st_off) * 2 + i] = a;
+    if (s_tot) s_tot[i] = a;                               // gn_stats_table_kernel goes on in this block: no global round trip
   }
   return true;
 }
@@ -369,10 +378,11 @@ __global__ void __launch_bounds__(1024) stats_finalize_kernel(const float* __res
 }
 
 // dynamic shared memory of gn_stats_block: float partials [lanes][C][2], reused as double run sums [segs][groups * 2]
-static inline size_t gn_stats_smem(int lanes, int C, int groups, int block) {
+static inline size_t gn_stats_smem(int lanes, int C, int groups, int block, bool with_totals = false) {
   int segs = block / (groups * 2); if (segs < 1) segs = 1; if (segs > 8) segs = 8;
   const size_t a = sizeof(float) * 2 * (size_t)lanes * C, r = sizeof(double) * (size_t)segs * groups * 2;
-  return a > r ? a : r;
+  const size_t m = ((a > r ? a : r) + 15) & ~(size_t)15;
+  return m + (with_totals ? sizeof(double) * (size_t)groups * 2 : 0);      // + [groups * 2] totals (gn_stats_table_kernel)
 }
 // scratch for block partials + ticket counters, grown on demand (single stream of use per device)
 struct StatsScratch { double* partial = nullptr; size_t cap = 0; unsigned int* tickets = nullptr; int tcap = 0; };
@@ -657,17 +667,32 @@ __global__ void __launch_bounds__(256, 1) gn_fused_kernel(const GnFusedP p) {
 // A-operand transform): table[b][c] = (scale, shift) with scale = gamma * rstd, shift = beta - mean * scale.
 // One block per image, one thread per channel; same double-precision group statistics as gn_apply_kernel.
 // table[b][c] = (scale, shift) of image b (all threads of the block; shared by gn_scale_shift_kernel and gn_stats_table_kernel)
+template <bool kSt0Shared>
 __device__ __forceinline__ void gn_table_block(const double* st0, int st0_ld, int c0, const double* st1, int st1_ld, int c1,
                                                const float* __restrict__ gamma, const float* __restrict__ beta, int64_t gb_bstride,
                                                double hw, int groups, float eps, float* __restrict__ table, int b,
                                                float* s_mean, float* s_rstd) {
+  // kSt0Shared: st0 points at THIS image's [c0][2] totals in shared memory (written by this block a moment ago)
   const int C = c0 + c1, cpg = C / groups;
+  // gamma / beta of this thread's first four channels: issued before the statistics math, consumed after it
+  float ga_r[4], be_r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = threadIdx.x + k * blockDim.x;
+    ga_r[k] = (gamma && c < C) ? gamma[(int64_t)b * gb_bstride + c] : 1.f;
+    be_r[k] = (beta && c < C) ? beta[(int64_t)b * gb_bstride + c] : 0.f;
+  }
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double a = 0.0, q = 0.0;
     for (int i = 0; i < cpg; ++i) {
       const int c = g * cpg + i;
-      const double* sp = c < c0 ? st0 + ((int64_t)b * st0_ld + c) * 2 : st1 + ((int64_t)b * st1_ld + (c - c0)) * 2;
-      a += __ldcg(sp); q += __ldcg(sp + 1);
+      if (c < c0) {
+        const double* sp = kSt0Shared ? st0 + (int64_t)c * 2 : st0 + ((int64_t)b * st0_ld + c) * 2;
+        if (kSt0Shared) { a += sp[0]; q += sp[1]; } else { a += __ldcg(sp); q += __ldcg(sp + 1); }
+      } else {
+        const double* sp = st1 + ((int64_t)b * st1_ld + (c - c0)) * 2;
+        a += __ldcg(sp); q += __ldcg(sp + 1);
+      }
     }
     const double cnt = hw * (double)cpg;
     const double m = a / cnt;
@@ -677,7 +702,17 @@ __device__ __forceinline__ void gn_table_block(const double* st0, int st0_ld, in
     s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = threadIdx.x + k * blockDim.x;
+    if (c < C) {
+      const int g = c / cpg;
+      const float sc = ga_r[k] * s_rstd[g];
+      table[((int64_t)b * C + c) * 2 + 0] = sc;
+      table[((int64_t)b * C + c) * 2 + 1] = be_r[k] - s_mean[g] * sc;
+    }
+  }
+  for (int c = threadIdx.x + 4 * blockDim.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
     const float ga = gamma ? gamma[(int64_t)b * gb_bstride + c] : 1.f;
     const float be = beta ? beta[(int64_t)b * gb_bstride + c] : 0.f;
@@ -691,7 +726,7 @@ __global__ void gn_scale_shift_kernel(const double* __restrict__ st0, int st0_ld
                                       int st1_ld, int c1, const float* __restrict__ gamma, const float* __restrict__ beta,
                                       int64_t gb_bstride, double hw, int groups, float eps, float* __restrict__ table) {
   __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
-  gn_table_block(st0, st0_ld, c0, st1, st1_ld, c1, gamma, beta, gb_bstride, hw, groups, eps, table, blockIdx.x, s_mean, s_rstd);
+  gn_table_block<false>(st0, st0_ld, c0, st1, st1_ld, c1, gamma, beta, gb_bstride, hw, groups, eps, table, blockIdx.x, s_mean, s_rstd);
 }
 
 // Statistics of x0 AND the folded (scale, shift) table of GroupNorm/AdaGN over [x0 | x1] in one launch: the last block of an
@@ -701,14 +736,14 @@ template <typename T>
 __global__ void __launch_bounds__(256, 3) gn_stats_table_kernel(const T* __restrict__ x0, int c0, int ld0, double* st0, int st0_ld,
                                 int c1, const double* st1, int st1_ld, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 int64_t gb_bstride, int64_t hw, int groups, float eps, float* __restrict__ table,
-                                double* partial, unsigned int* tickets, int GN_PPB) {
+                                double* partial, unsigned int* tickets, int GN_PPB, unsigned int tot_off) {
   extern __shared__ float s_part[];
   __shared__ float s_mean[GN_MAX_C / 4], s_rstd[GN_MAX_C / 4];
   __shared__ bool s_last;
-  if (!gn_stats_block<T>(x0, c0, ld0, nullptr, 0, 0, hw, c0, st0, st0_ld, 0, partial, tickets, GN_PPB, s_part, &s_last)) return;
-  __threadfence();
-  __syncthreads();                               // the totals written by this block's threads are visible to all of them
-  gn_table_block(st0, st0_ld, c0, st1, st1_ld, c1, gamma, beta, gb_bstride, (double)hw, groups, eps, table, blockIdx.y, s_mean, s_rstd);
+  double* s_tot = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_part) + tot_off);     // [c0 * 2] totals of this image
+  if (!gn_stats_block<T>(x0, c0, ld0, nullptr, 0, 0, hw, c0, st0, st0_ld, 0, partial, tickets, GN_PPB, s_part, &s_last, s_tot)) return;
+  __syncthreads();                               // the totals (shared memory) are visible to all threads of this block
+  gn_table_block<true>(s_tot, 0, c0, st1, st1_ld, c1, gamma, beta, gb_bstride, (double)hw, groups, eps, table, blockIdx.y, s_mean, s_rstd);
 }
 
 __global__ void gap_mean_kernel(const double* __restrict__ stats, float* __restrict__ out, int n, double inv) {
@@ -806,15 +841,17 @@ extern "C" int mudiff_gn_stats_table(const void* x0, int c0, int ld0, int dtype,
   if (dev < 0 || dev >= 16) return MUDIFF_EUNSUPPORTED;
   int rc = ensure_scratch(dev, (size_t)batch * chunks * c0 * 2, batch, st);
   if (rc) return rc;
-  const size_t smem = gn_stats_smem(lanes, c0, c0, block);
+  const size_t smem = gn_stats_smem(lanes, c0, c0, block, true);
+  const unsigned int tot_off = (unsigned int)gn_stats_smem(lanes, c0, c0, block);
+  if (smem > 48 * 1024) return MUDIFF_EUNSUPPORTED;
   if (dtype == MUDIFF_BF16)
     gn_stats_table_kernel<__nv_bfloat16><<<dim3(chunks, batch), block, smem, st>>>(
         (const __nv_bfloat16*)x0, c0, ld0, st0, st0_ld, c1, st1, st1_ld, gamma, beta, gb_bstride, hw, groups, eps, table,
-        g_scratch[dev].partial, g_scratch[dev].tickets, ppb);
+        g_scratch[dev].partial, g_scratch[dev].tickets, ppb, tot_off);
   else
     gn_stats_table_kernel<float><<<dim3(chunks, batch), block, smem, st>>>(
         (const float*)x0, c0, ld0, st0, st0_ld, c1, st1, st1_ld, gamma, beta, gb_bstride, hw, groups, eps, table,
-        g_scratch[dev].partial, g_scratch[dev].tickets, ppb);
+        g_scratch[dev].partial, g_scratch[dev].tickets, ppb, tot_off);
   return mudiff_launch_status();
 }
 
