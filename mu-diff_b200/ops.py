@@ -18,6 +18,7 @@ _ENV_FLAGS = 2 if _os.environ.get('MUDIFF_HALO', '1') == '0' else 0     # debug 
 _ENV_FLAGS |= int(_os.environ.get('MUDIFF_XF_DBG', '0')) << 20        # timing ablations of the operand transform
 _ENV_FLAGS |= 1024 if _os.environ.get('MUDIFF_BCAP12', '0') == '1' else 0   # ablation: the older, larger B ring (12 sub-tiles)
 _ENV_FLAGS |= 0x400000 if _os.environ.get('MUDIFF_NT128', '1') == '0' else 0   # ablation: N = 384 as two 192-column tiles (one accumulator stage) instead of three of 128
+_ENV_FLAGS |= int(_os.environ.get('MUDIFF_CONV_DBG_FLAGS', '0'), 0)    # timing ablations only (64: no operand traffic, 128: no epilogue - WRONG RESULTS)
 
 # Fused epilogue statistics (conv_tc butterfly reduction) are implemented and tested, but since the MMA issue
 # loop got fast they cost more than the stand-alone HBM-bound statistics pass for every N <= 256 (measured,
