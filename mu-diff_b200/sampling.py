@@ -97,7 +97,7 @@ def sample_from_model(coefficients, generator1, cond1, generator2, cond2, cond3,
     The reference's autocast() context is replaced by the generators' own precision switch."""
     x = x_init
     conds = [c for c in (cond1, cond2, cond3) if c is not None]
-    with torch.no_grad():
+    with torch.no_grad(), ops.stem_moments_scope():
         for i in reversed(range(n_time)):
             t = torch.full((x.size(0),), i, dtype=torch.int64, device=x.device)
             latent_z = latents[i] if latents is not None else torch.randn(x.size(0), opt.nz, device=x.device)
@@ -140,7 +140,7 @@ class GraphSampler:
 
     def _loop(self):
         x = self.x_init
-        with torch.no_grad():
+        with torch.no_grad(), ops.stem_moments_scope():
             for i in reversed(range(self.n_time)):
                 x01 = self.g1(x, *self.conds, self.ts[i], self.latents[i])
                 x02 = self.g2(x, *self.conds, self.ts[i], self.latents[i], _ch0(x01))      # engine/test.py:193

@@ -243,6 +243,31 @@ def test_full_size_256_bf16_and_fp32_vs_oracle(M):
         assert torch.equal(xg, x3)                                # graph replay == eager, bit for bit
 
 
+def test_stem_moments_scope_is_identical_and_saves_launches(M):
+    """ops.stem_moments_scope (active inside sample_from_model / GraphSampler): the input second moments of the conditioning
+    contrasts and of x_t are computed once per distinct tensor instead of once per stem - 36 -> 11 mudiff_stem_moments launches
+    per 4-step sample of the 3-contrast generators - with bit-identical outputs."""
+    cfg = O.default_config(num_channels_dae=64, image_size=64)
+    ns, g1, g2, _, _ = _build(M, cfg, 'bf16')
+    co = M.Posterior_Coefficients(ns, DEV)
+    conds, x_init, latents, noises = O.synthetic_inputs(2, 64, cfg, seed=5)
+    c, x0, z, e = _to(conds), x_init.to(DEV), _to(latents), _to(noises)
+    n0 = M._lib.launch_count()
+    y = M.sample_from_model(co, g1, c[0], g2, c[1], c[2], cfg.num_timesteps, x0, None, ns, latents=z, noises=e)
+    n1 = M._lib.launch_count()
+    x = x0
+    with torch.no_grad():                                   # the same loop without the scope
+        for i in reversed(range(cfg.num_timesteps)):
+            t = torch.full((x.size(0),), i, dtype=torch.int64, device=DEV)
+            x01 = g1(x, *c, t, z[i])
+            x02 = g2(x, *c, t, z[i], x01[:, 0:1])
+            x = M.sample_posterior_combine(co, x01[:, 0:1], x02[:, 0:1], x, t, noise=e[i])
+    n2 = M._lib.launch_count()
+    torch.cuda.synchronize()
+    assert torch.equal(x, y)
+    assert (n2 - n1) - (n1 - n0) == 25, (n1 - n0, n2 - n1)
+
+
 def test_streaming_sampler_equals_sequential(M):
     """sampling.StreamingSampler (H2D / D2H of neighbouring batches overlapped with the graph replay on copy streams):
     five different host batches, the last one ragged, give bit for bit what the sequential copy -> draw -> replay -> copy
