@@ -631,6 +631,12 @@ class stem_moments_scope:
         return False
 
 
+def loop_scope():
+    """The dict of the active stem_moments_scope (one pass of the sampling loop), or None.  Also used by the generators to keep
+    what does not change between the diffusion steps of a sample (_generator._stem)."""
+    return _MOM_SCOPE
+
+
 def stem_conv_gn_act(x, wt9, bias, groups, *, gamma=None, beta=None, gb_bstride=0, eps=1e-6, act=L.ACT_SILU,
                      out_dtype=torch.bfloat16):
     """act(GroupNorm(conv3x3(x))) for a 1-channel input (the stems of ConvFeatBlock / ConvBlock / ConvBlock_GAP,

@@ -246,7 +246,8 @@ def test_full_size_256_bf16_and_fp32_vs_oracle(M):
 def test_stem_moments_scope_is_identical_and_saves_launches(M):
     """ops.stem_moments_scope (active inside sample_from_model / GraphSampler): the input second moments of the conditioning
     contrasts and of x_t are computed once per distinct tensor instead of once per stem - 36 -> 11 mudiff_stem_moments launches
-    per 4-step sample of the 3-contrast generators - with bit-identical outputs."""
+    per 4-step sample of the 3-contrast generators - and G1's t- and z-independent ConvFeatBlock features of the conditioning
+    contrasts once per sample instead of once per step, with bit-identical outputs."""
     cfg = O.default_config(num_channels_dae=64, image_size=64)
     ns, g1, g2, _, _ = _build(M, cfg, 'bf16')
     co = M.Posterior_Coefficients(ns, DEV)
@@ -265,7 +266,9 @@ def test_stem_moments_scope_is_identical_and_saves_launches(M):
     n2 = M._lib.launch_count()
     torch.cuda.synchronize()
     assert torch.equal(x, y)
-    assert (n2 - n1) - (n1 - n0) == 25, (n1 - n0, n2 - n1)
+    saved = (n2 - n1) - (n1 - n0)
+    print(f"[loop scope] launches per 4-step sample: {n2 - n1} without the scope, {n1 - n0} with it ({saved} saved)")
+    assert saved >= 25, (n1 - n0, n2 - n1)       # 25 stem_moments launches + G1's conditioning stems of the three later steps
 
 
 def test_streaming_sampler_equals_sequential(M):
