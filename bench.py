@@ -80,7 +80,8 @@ def ncu_traffic():
     if not per:
         return None, "capture has no dram__bytes rows"
     return sum(per.values()) / len(per), (f"mean DRAM bytes (read + write) per conv_tc launch over the {len(per)} conv_tc launches "
-                                          "of one eager step of this workload, ncu capture profiles/r02_conv_tc_dram.csv")
+                                          "of one eager step of this workload, ncu capture profiles/r02_conv_tc_dram.csv (taken before the nine "
+                                          "step-invariant 64->64 stem convs per step were removed; same kernels and shapes)")
 
 
 class ClockSampler(threading.Thread):
