@@ -161,3 +161,24 @@ def test_pack_cache_refreshes_in_place():
     conv.load_state_dict({'weight': torch.ones_like(conv.weight), 'bias': torch.zeros_like(conv.bias)})
     assert conv.packed_weight(torch.bfloat16).data_ptr() == ptr_w
     assert float(conv.packed_weight(torch.bfloat16).float().min()) == 1.0
+
+
+def test_loop_scope_nesting_and_cleanup():
+    """ops.stem_moments_scope (the per-sample scope of the sampling loop): nothing is cached outside it, nested scopes share
+    one dict, and the scope is closed again when the loop raises."""
+    from mudiff_b200 import ops
+    assert ops.loop_scope() is None
+    with ops.stem_moments_scope():
+        d = ops.loop_scope()
+        assert d == {}
+        d['k'] = 1
+        with ops.stem_moments_scope():
+            assert ops.loop_scope() is d
+        assert ops.loop_scope() is d
+    assert ops.loop_scope() is None
+    with pytest.raises(ValueError):
+        with ops.stem_moments_scope():
+            raise ValueError('loop failed')
+    assert ops.loop_scope() is None
+    with ops.stem_moments_scope():
+        assert ops.loop_scope() == {}          # a new sample starts with an empty scope
